@@ -1,0 +1,77 @@
+// Shared helpers for libfdm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/fdm_b200.h"
+
+void fdm_set_error(const char* fmt, ...);
+
+#define FDM_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      fdm_set_error(__VA_ARGS__);           \
+      return 1;                             \
+    }                                       \
+  } while (0)
+
+#define FDM_CHECK_CUDA(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      fdm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define FDM_CHECK_LAUNCH() FDM_CHECK_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int fdm_sm_count();  // cached multiprocessor count of the current device
+
+// ---- dtype-generic loads / stores (fp32 math everywhere) --------------------------------------
+__device__ __forceinline__ float ld_as_float(const void* p, int32_t dtype, int64_t i) {
+  return dtype == FDM_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                           : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_from_float(void* p, int32_t dtype, int64_t i, float v) {
+  if (dtype == FDM_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
+// ---- activations (match the PyTorch definitions used by the reference) -------------------------
+__device__ __forceinline__ float act_mish(float x) {
+  // x * tanh(softplus(x)), softplus threshold 20 as in ATen
+  float sp = x > 20.f ? x : log1pf(expf(x));
+  return x * tanhf(sp);
+}
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float act_gelu_tanh(float x) {
+  // models/utils/base_model_util.py:81-94
+  float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return x * (0.5f * (1.f + tanhf(inner)));
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case FDM_ACT_RELU: return x > 0.f ? x : 0.f;
+    case FDM_ACT_MISH: return act_mish(x);
+    case FDM_ACT_GELU_ERF: return act_gelu_erf(x);
+    case FDM_ACT_GELU_TANH: return act_gelu_tanh(x);
+    case FDM_ACT_LEAKY02: return x > 0.f ? x : 0.2f * x;
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

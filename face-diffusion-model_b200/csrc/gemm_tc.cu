@@ -1,0 +1,464 @@
+// fdm_gemm_bf16: persistent, warp-specialised tcgen05/TMEM GEMM fed by TMA (sm_100a).
+//
+//   C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual          bf16 operands, fp32 accumulate
+//
+// Both operands are K-major (activation rows and nn.Linear weights), so A and W tiles are loaded by
+// TMA straight into the 128B-swizzled K-major layout tcgen05.mma consumes; no transposes anywhere.
+// Implicit 1-D convolutions (VQ-decoder Conv1d k5, HuBERT conv stack / positional conv) are the same
+// kernel: the producer shifts the TMA row coordinate per filter tap instead of materialising im2col.
+//
+// CTA layout (192 threads, 1 CTA/SM, persistent over a static tile schedule):
+//   warp 0      TMA producer   (one elected lane)         smem ring: STAGES x {A 128x64, W BLOCK_Nx64}
+//   warp 1      MMA issuer     (one elected lane)         tcgen05.mma 128 x BLOCK_N x 16, cta_group::1
+//   warps 2-5   epilogue       (TMEM lane quadrant = warp & 3), double-buffered TMEM accumulator
+// Pipelines: full/empty mbarriers (TMA <-> MMA), tmem_full/tmem_empty mbarriers (MMA <-> epilogue).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int ACC_STAGES = 2;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+};
+
+struct Epilogue {
+  const float* bias;
+  const void* residual;
+  void* C;
+  int64_t ldr, ldc;
+  int32_t res_dtype, out_dtype, act;
+  int32_t vec_c, vec_r, vec_bias;  // 16-byte vector access is legal for full 32-column chunks
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) {  // watchdog: a protocol bug must trap, never hang the GPU
+      printf("fdm gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (ignored for swizzled K-major) | [32,46) SBO>>4 = 1024B (8 rows x 128B)
+//   [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, K-major A and B.
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
+  return (1u << 4)                              // c_format = F32
+         | (1u << 7)                            // a_format = BF16
+         | (1u << 10)                           // b_format = BF16
+         | (0u << 15) | (0u << 16)              // a_major, b_major = K
+         | (static_cast<uint32_t>(n >> 3) << 17)
+         | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- epilogue: one thread owns one output row, 32 consecutive columns per chunk -------------------
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const Epilogue& ep, int64_t row, int col0, int N) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  const int ncols = min(32, N - col0);
+  const bool full = ncols == 32;
+
+  if (ep.bias) {
+    if (full && ep.vec_bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += __ldg(ep.bias + col0 + j);
+    }
+  }
+  if (ep.act != FDM_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+  }
+  if (ep.residual) {
+    if (ep.res_dtype == FDM_BF16) {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + row * ep.ldr + col0;
+      if (full && ep.vec_r) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u = __ldg(r4 + j);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 f = __bfloat1622float2(h[q]);
+            v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) v[j] += __bfloat162float(r[j]);
+      }
+    } else {
+      const float* r = reinterpret_cast<const float*>(ep.residual) + row * ep.ldr + col0;
+      if (full && ep.vec_r) {
+        const float4* r4 = reinterpret_cast<const float4*>(r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b = __ldg(r4 + j);
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) v[j] += r[j];
+      }
+    }
+  }
+  if (ep.out_dtype == FDM_BF16) {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ldc + col0;
+    if (full && ep.vec_c) {
+      uint4* c4 = reinterpret_cast<uint4*>(c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+        c4[j] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* c = reinterpret_cast<float*>(ep.C) + row * ep.ldc + col0;
+    if (full && ep.vec_c) {
+      float4* c4 = reinterpret_cast<float4*>(c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c[j] = v[j];
+    }
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
+               const int tap_row_shift, const int m_tiles, const int n_tiles) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + ACC_STAGES + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 2 * ACC_STAGES));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const int tap = kb / kb_per_tap;
+          const int kc = kb - tap * kb_per_tap;
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kc * BLOCK_K, m_blk * BLOCK_M + tap * tap_row_shift);
+          tma_load_2d(sa + C::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+            umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global =====
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * BLOCK_M + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tmem_ld_wait();
+        if (row < M) epilogue_chunk(r, ep, row, col0, N);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner extent `cols` (contiguous), `rows` rows with `ld` elements between rows,
+// box = 64 x box_rows, 128-byte swizzle, out-of-bounds reads return zero.
+int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int64_t ld, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  FDM_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FDM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld ld=%lld)",
+                static_cast<int>(r), (long long)cols, (long long)rows, (long long)ld);
+  return 0;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int BLOCK_N>
+int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int taps = a.taps > 1 ? a.taps : 1;
+  const int64_t a_cols = taps > 1 ? a.tap_k : a.K;
+  CUtensorMap tm_a, tm_b;
+  if (int rc = make_tmap(&tm_a, a.A, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
+  if (int rc = make_tmap(&tm_b, a.W, a.K, a.N, a.ldw, BLOCK_N)) return rc;
+  const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M));
+  const int n_tiles = static_cast<int>(ceil_div64(a.N, BLOCK_N));
+  const int num_k_blocks = static_cast<int>(ceil_div64(a.K, BLOCK_K));
+  const int kb_per_tap = taps > 1 ? static_cast<int>(a.tap_k / BLOCK_K) : num_k_blocks;
+  const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
+  const int grid = static_cast<int>(tiles < fdm_sm_count() ? tiles : fdm_sm_count());
+  gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(
+      tm_a, tm_b, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
+      taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
+  FDM_CHECK_ARG(args != nullptr, "fdm_gemm_bf16: null args");
+  const fdm_gemm_args& a = *args;
+  FDM_CHECK_ARG(a.A && a.W && a.C, "fdm_gemm_bf16: null operand");
+  FDM_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "fdm_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)a.M, (long long)a.N, (long long)a.K);
+  FDM_CHECK_ARG(a.M < (1ll << 31) && a.N < (1ll << 31) && a.K < (1ll << 31), "fdm_gemm_bf16: dimension too large");
+  FDM_CHECK_ARG(aligned16(a.A) && aligned16(a.W), "fdm_gemm_bf16: A and W must be 16-byte aligned");
+  FDM_CHECK_ARG(a.lda % 8 == 0 && a.ldw % 8 == 0, "fdm_gemm_bf16: lda/ldw must be multiples of 8 elements (TMA 16-byte strides)");
+  FDM_CHECK_ARG(a.a_rows >= a.M, "fdm_gemm_bf16: a_rows < M");
+  if (a.taps > 1) {
+    FDM_CHECK_ARG(a.tap_k > 0 && a.tap_k % BLOCK_K == 0 && a.K == a.taps * a.tap_k,
+                  "fdm_gemm_bf16: implicit conv needs K == taps*tap_k and tap_k %% 64 == 0");
+  }
+  FDM_CHECK_ARG(a.out_dtype == FDM_F32 || a.out_dtype == FDM_BF16, "fdm_gemm_bf16: bad out_dtype");
+  Epilogue ep;
+  ep.bias = a.bias;
+  ep.residual = a.residual;
+  ep.C = a.C;
+  ep.ldr = a.ldr;
+  ep.ldc = a.ldc;
+  ep.res_dtype = a.res_dtype;
+  ep.out_dtype = a.out_dtype;
+  ep.act = a.act;
+  const int64_t csz = a.out_dtype == FDM_BF16 ? 2 : 4, rsz = a.res_dtype == FDM_BF16 ? 2 : 4;
+  ep.vec_c = aligned16(a.C) && (a.ldc * csz) % 16 == 0;
+  ep.vec_r = a.residual && aligned16(a.residual) && (a.ldr * rsz) % 16 == 0;
+  ep.vec_bias = a.bias && aligned16(a.bias);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+  // Tile width: the widest tile that still yields at least one tile per SM; narrow problems fall to 64.
+  const int64_t m_tiles = ceil_div64(a.M, BLOCK_M);
+  const int sms = fdm_sm_count();
+  if (a.N >= 256 && m_tiles * ceil_div64(a.N, 256) >= sms) return launch<256>(a, ep, s);
+  if (a.N >= 128 && m_tiles * ceil_div64(a.N, 128) >= sms) return launch<128>(a, ep, s);
+  if (a.N > 64 && a.N % 64 != 0 && a.N >= 128) return launch<128>(a, ep, s);
+  return launch<64>(a, ep, s);
+}

@@ -1,0 +1,137 @@
+// Small data-movement kernels around the GEMMs: casts, the (B,C,L)->(B,L,C) transpose of VQAutoEncoder.decode,
+// per-clip time padding for the implicit convolutions, and HuBERT's first conv layer (1 input channel).
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) cast_kernel(const void* src, int sd, void* dst, int dd, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    st_from_float(dst, dd, i, ld_as_float(src, sd, i));
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float* src, void* dst, int dd, int C, int L) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    tile[i][tx] = (c < C && l < L) ? src[(b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    if (l < L && c < C) st_from_float(dst, dd, (b * L + l) * C + c, tile[tx][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) pad_time_kernel(const void* src, int64_t src_t_stride, void* dst, int dtype, int T, int C,
+                                                       int pad_l, int pad_r, int mode) {
+  const int64_t b = blockIdx.y;
+  const int P = pad_l + T + pad_r;
+  const int64_t n = static_cast<int64_t>(P) * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<int64_t>(p) * C);
+    int t = p - pad_l;
+    float v = 0.f;
+    if (mode == 1) t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+    if (t >= 0 && t < T) v = ld_as_float(src, dtype, (b * src_t_stride + t) * C + c);
+    st_from_float(dst, dtype, b * n + i, v);
+  }
+}
+
+// one warp per output frame; C <= 1024 channels, C % 32 == 0
+template <int CPL>  // channels per lane
+__global__ void __launch_bounds__(256) hubert_conv0_kernel(const float* __restrict__ audio, int64_t L, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ g,
+                                                           const float* __restrict__ beta, void* out, int od, int Lout,
+                                                           int64_t out_t_stride) {
+  constexpr int C = CPL * 32;
+  __shared__ float ws[C * 10];
+  for (int i = threadIdx.x; i < C * 10; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.y;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= out_t_stride) return;
+  const int64_t orow = (b * out_t_stride + t) * C;
+  if (t >= Lout) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) st_from_float(out, od, orow + lane + 32 * j, 0.f);
+    return;
+  }
+  float x[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) x[k] = audio[b * L + t * 5 + k];
+  float v[CPL];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc = fmaf(ws[c * 10 + k], x[k], acc);
+    v[j] = acc + bias[c];
+    s += v[j];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) q += (v[j] - mean) * (v[j] - mean);
+  const float rstd = 1.f / sqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    st_from_float(out, od, orow + c, act_gelu_erf((v[j] - mean) * rstd * g[c] + beta[c]));
+  }
+}
+
+inline int grid1d(int64_t n) {
+  const int64_t want = ceil_div64(n, 256), cap = static_cast<int64_t>(fdm_sm_count()) * 8;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int fdm_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+  FDM_CHECK_ARG(src && dst && n >= 0, "fdm_cast: bad arguments");
+  if (n == 0) return 0;
+  cast_kernel<<<grid1d(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_dtype, dst, dst_dtype, n);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_transpose_bcl_to_blc(const float* src, void* dst, int32_t dst_dtype, int64_t B, int64_t C, int64_t L, void* stream) {
+  FDM_CHECK_ARG(src && dst && B > 0 && C > 0 && L > 0 && B <= 65535 && C <= 65535 * 32, "fdm_transpose_bcl_to_blc: bad arguments");
+  dim3 grid(static_cast<unsigned>(ceil_div64(L, 32)), static_cast<unsigned>(ceil_div64(C, 32)), static_cast<unsigned>(B));
+  transpose_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, dst_dtype, static_cast<int>(C), static_cast<int>(L));
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_pad_time(const void* src, int64_t src_t_stride, void* dst, int32_t dtype, int64_t B, int64_t T, int64_t C,
+                            int64_t pad_l, int64_t pad_r, int32_t mode, void* stream) {
+  FDM_CHECK_ARG(src && dst && B > 0 && T > 0 && C > 0 && pad_l >= 0 && pad_r >= 0 && B <= 65535 && src_t_stride >= T,
+                "fdm_pad_time: bad arguments");
+  dim3 grid(static_cast<unsigned>(grid1d((pad_l + T + pad_r) * C)), static_cast<unsigned>(B));
+  pad_time_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_t_stride, dst, dtype, static_cast<int>(T),
+                                                                            static_cast<int>(C), static_cast<int>(pad_l),
+                                                                            static_cast<int>(pad_r), mode);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_hubert_conv0(const float* audio, int64_t B, int64_t L, const float* w, const float* bias, const float* ln_g,
+                                const float* ln_b, void* out, int32_t out_dtype, int64_t Lout, int64_t out_t_stride, int64_t C,
+                                void* stream) {
+  FDM_CHECK_ARG(audio && w && bias && ln_g && ln_b && out, "fdm_hubert_conv0: null operand");
+  FDM_CHECK_ARG(B > 0 && B <= 65535 && Lout > 0 && out_t_stride >= Lout && (Lout - 1) * 5 + 10 <= L, "fdm_hubert_conv0: bad sizes");
+  dim3 grid(static_cast<unsigned>(ceil_div64(out_t_stride, 8)), static_cast<unsigned>(B));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 512) hubert_conv0_kernel<16><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
+  else if (C == 32) hubert_conv0_kernel<1><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
+  else if (C == 64) hubert_conv0_kernel<2><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
+  else FDM_CHECK_ARG(false, "fdm_hubert_conv0: C=%lld not in {32,64,512}", (long long)C);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}

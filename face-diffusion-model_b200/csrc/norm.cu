@@ -1,0 +1,188 @@
+// Row LayerNorm with fused residual adds (one warp per row, values kept in registers, two-pass
+// mean/variance in fp32) and LeakyReLU + InstanceNorm over time for the VQ-decoder expander.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_V4 = 8;  // float4 groups per lane -> d <= 32*4*8 = 1024
+
+__device__ __forceinline__ float4 load4(const void* p, int dtype, int64_t idx) {
+  if (dtype == FDM_BF16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx);
+}
+__device__ __forceinline__ void store4(void* p, int dtype, int64_t idx, float4 v) {
+  if (dtype == FDM_BF16) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(v.x, v.y);
+    h[1] = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + idx) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = v;
+  }
+}
+
+__device__ __forceinline__ void ln_inplace(float4 (&v)[MAX_V4], int nv, int lane, int d, float eps, const float* g,
+                                           const float* b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv && (i * 32 + lane) * 4 < d) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv && (i * 32 + lane) * 4 < d) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + e * e);
+    }
+  const float rstd = 1.f / sqrtf(warp_sum(q) / static_cast<float>(d) + eps);
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i)
+    if (i < nv && (i * 32 + lane) * 4 < d) {
+      const int c0 = (i * 32 + lane) * 4;
+      const float4 gg = *reinterpret_cast<const float4*>(g + c0);
+      const float4 bv = *reinterpret_cast<const float4*>(b + c0);
+      v[i].x = (v[i].x - mean) * rstd * gg.x + bv.x;
+      v[i].y = (v[i].y - mean) * rstd * gg.y + bv.y;
+      v[i].z = (v[i].z - mean) * rstd * gg.z + bv.z;
+      v[i].w = (v[i].w - mean) * rstd * gg.w + bv.w;
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const fdm_norm_args a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  const int d = static_cast<int>(a.d);
+  const int nv = (d + 127) / 128;
+  float4 v[MAX_V4];
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    if (i < nv && c0 < d) {
+      v[i] = load4(a.x, a.x_dtype, row * a.ldx + c0);
+      if (a.r1) {
+        const float4 r = load4(a.r1, a.r1_dtype, row * a.ldr1 + c0);
+        v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+      }
+    }
+  }
+  if (a.g1) ln_inplace(v, nv, lane, d, a.eps, a.g1, a.b1);
+  if (a.act1 != FDM_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i)
+      if (i < nv && (i * 32 + lane) * 4 < d) {
+        v[i].x = apply_act(v[i].x, a.act1); v[i].y = apply_act(v[i].y, a.act1);
+        v[i].z = apply_act(v[i].z, a.act1); v[i].w = apply_act(v[i].w, a.act1);
+      }
+  }
+  if (a.g2) {
+    const float* vec = a.vec2 ? a.vec2 + static_cast<int64_t>(*a.vec_index_dev) * d : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAX_V4; ++i) {
+      const int c0 = (i * 32 + lane) * 4;
+      if (i < nv && c0 < d) {
+        if (a.r2) {
+          const float4 r = load4(a.r2, a.r2_dtype, row * a.ldr2 + c0);
+          v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+        }
+        if (vec) {
+          const float4 r = *reinterpret_cast<const float4*>(vec + c0);
+          v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+        }
+      }
+    }
+    ln_inplace(v, nv, lane, d, a.eps, a.g2, a.b2);
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_V4; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    if (i < nv && c0 < d) {
+      store4(a.out, a.out_dtype, row * a.ldo + c0, v[i]);
+      if (a.out2) store4(a.out2, a.out2_dtype, row * a.ldo2 + c0, v[i]);
+    }
+  }
+}
+
+// block = 32 channels x 8 time-lanes; grid = (C/32, B)
+__global__ void __launch_bounds__(256) leaky_instnorm_kernel(const void* x, int x_dtype, void* out, int out_dtype, int T,
+                                                             int64_t t_stride, int C, float slope, float eps) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int64_t base = static_cast<int64_t>(blockIdx.y) * t_stride * C;
+  const bool ok = c < C;
+  float s = 0.f;
+  for (int t = ty; t < T; t += 8)
+    if (ok) {
+      float v = ld_as_float(x, x_dtype, base + static_cast<int64_t>(t) * C + c);
+      s += v > 0.f ? v : slope * v;
+    }
+  red[ty][cx] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i][cx];
+  const float mean = tot / static_cast<float>(T);
+  __syncthreads();
+  float q = 0.f;
+  for (int t = ty; t < T; t += 8)
+    if (ok) {
+      float v = ld_as_float(x, x_dtype, base + static_cast<int64_t>(t) * C + c);
+      v = (v > 0.f ? v : slope * v) - mean;
+      q += v * v;
+    }
+  red[ty][cx] = q;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i][cx];
+  const float rstd = 1.f / sqrtf(tot / static_cast<float>(T) + eps);
+  for (int t = ty; t < T; t += 8)
+    if (ok) {
+      float v = ld_as_float(x, x_dtype, base + static_cast<int64_t>(t) * C + c);
+      v = (v > 0.f ? v : slope * v);
+      st_from_float(out, out_dtype, base + static_cast<int64_t>(t) * C + c, (v - mean) * rstd);
+    }
+}
+
+inline bool ok_align(const void* p, int dtype, int64_t ld) {
+  const uintptr_t a = dtype == FDM_BF16 ? 8 : 16;
+  return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % a) == 0 && ld % 4 == 0);
+}
+
+}  // namespace
+
+extern "C" int fdm_layernorm(const fdm_norm_args* args, void* stream) {
+  FDM_CHECK_ARG(args != nullptr, "fdm_layernorm: null args");
+  const fdm_norm_args& a = *args;
+  FDM_CHECK_ARG(a.x && a.out, "fdm_layernorm: null x/out");
+  FDM_CHECK_ARG(a.rows >= 0 && a.d > 0 && a.d % 4 == 0 && a.d <= 128 * MAX_V4, "fdm_layernorm: d=%lld must be a multiple of 4 and <= %d",
+                (long long)a.d, 128 * MAX_V4);
+  FDM_CHECK_ARG(ok_align(a.x, a.x_dtype, a.ldx) && ok_align(a.r1, a.r1_dtype, a.ldr1) && ok_align(a.r2, a.r2_dtype, a.ldr2) &&
+                    ok_align(a.out, a.out_dtype, a.ldo) && ok_align(a.out2, a.out2_dtype, a.ldo2),
+                "fdm_layernorm: operands must be vector-aligned with strides %% 4 == 0");
+  FDM_CHECK_ARG(!a.vec2 || a.vec_index_dev, "fdm_layernorm: vec2 needs vec_index_dev");
+  FDM_CHECK_ARG((!a.g1 || a.b1) && (!a.g2 || a.b2), "fdm_layernorm: gamma without beta");
+  if (a.rows == 0) return 0;
+  const int warps = 8;
+  layernorm_kernel<<<static_cast<unsigned>(ceil_div64(a.rows, warps)), warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int32_t out_dtype, int64_t B, int64_t T,
+                                  int64_t t_stride, int64_t C, float slope, float eps, void* stream) {
+  FDM_CHECK_ARG(x && out && B > 0 && T > 0 && C > 0 && t_stride >= T, "fdm_leaky_instnorm: bad arguments");
+  dim3 grid(static_cast<unsigned>(ceil_div64(C, 32)), static_cast<unsigned>(B));
+  leaky_instnorm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, out, out_dtype, static_cast<int>(T),
+                                                                                  t_stride, static_cast<int>(C), slope, eps);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}

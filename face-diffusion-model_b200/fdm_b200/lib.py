@@ -1,0 +1,311 @@
+"""ctypes binding of libfdm_b200.so (C ABI declared in include/fdm_b200.h).
+
+PyTorch is used only for device memory and streams: every wrapper takes torch CUDA tensors, passes
+``data_ptr()`` + explicit sizes/strides to the library and launches on torch's current stream.
+There is no CPU or eager fallback: a missing library or a non-sm_100 device is a hard error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfdm_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU_ERF, ACT_GELU_TANH, ACT_LEAKY02 = range(6)
+
+_vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", _vp), ("lda", _i64), ("a_rows", _i64), ("W", _vp), ("ldw", _i64), ("bias", _vp),
+                ("residual", _vp), ("ldr", _i64), ("res_dtype", _i32), ("out_dtype", _i32), ("C", _vp),
+                ("ldc", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("act", _i32), ("taps", _i32),
+                ("tap_k", _i64), ("tap_row_shift", _i64)]
+
+
+class NormArgs(C.Structure):
+    _fields_ = [("x", _vp), ("ldx", _i64), ("x_dtype", _i32), ("r1", _vp), ("ldr1", _i64), ("r1_dtype", _i32),
+                ("g1", _vp), ("b1", _vp), ("act1", _i32), ("r2", _vp), ("ldr2", _i64), ("r2_dtype", _i32),
+                ("vec2", _vp), ("vec_index_dev", _vp), ("g2", _vp), ("b2", _vp), ("out", _vp), ("ldo", _i64),
+                ("out_dtype", _i32), ("out2", _vp), ("ldo2", _i64), ("out2_dtype", _i32), ("rows", _i64),
+                ("d", _i64), ("eps", _f32)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("Q", _vp), ("K", _vp), ("V", _vp), ("ldq", _i64), ("ldk", _i64), ("ldv", _i64), ("O", _vp),
+                ("ldo", _i64), ("dtype", _i32), ("B", _i64), ("T", _i64), ("t_stride", _i64), ("H", _i64),
+                ("dh", _i64), ("scale", _f32), ("bias_mode", _i32), ("period", _i32), ("slopes", _vp)]
+
+
+class DdpmArgs(C.Structure):
+    _fields_ = [("x0_cond", _vp), ("x0_uncond", _vp), ("guidance", _f32), ("x_t", _vp), ("noise", _vp),
+                ("out", _vp), ("out_bf16", _vp), ("c1", _vp), ("c2", _vp), ("sigma", _vp), ("t_per_clip", _vp),
+                ("t_sched", _vp), ("cursor_dev", _vp), ("B", _i64), ("elems_per_clip", _i64), ("seed", _u64),
+                ("clip_index0", _i64)]
+
+
+EXPORTS = {
+    "fdm_last_error": (C.c_char_p, []),
+    "fdm_device_info": (C.c_int, [C.POINTER(_i32)] * 3),
+    "fdm_abi_version": (C.c_int, []),
+    "fdm_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "fdm_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "fdm_layernorm": (C.c_int, [C.POINTER(NormArgs), _vp]),
+    "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
+    "fdm_self_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "fdm_ddpm_step": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
+    "fdm_advance_cursor": (C.c_int, [_vp, _vp]),
+    "fdm_philox_normal": (C.c_int, [_vp, _i64, _i64, _u64, _i64, _i32, _vp]),
+    "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
+    "fdm_transpose_bcl_to_blc": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "fdm_pad_time": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
+    "fdm_hubert_conv0": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp]),
+}
+
+_lib = None
+_device_checked = False
+
+
+class FdmError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the library and bind every symbol include/fdm_b200.h declares (no GPU needed)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FdmError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def require_device() -> C.CDLL:
+    """Library + an sm_100 device, or raise."""
+    global _device_checked
+    lib = load()
+    if not _device_checked:
+        if not torch.cuda.is_available():
+            raise FdmError("libfdm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        sm, mj, mn = _i32(), _i32(), _i32()
+        _check(lib.fdm_device_info(C.byref(sm), C.byref(mj), C.byref(mn)))
+        _device_checked = True
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise FdmError(load().fdm_last_error().decode())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise FdmError(f"unsupported dtype {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "libfdm_b200 operates on CUDA tensors only"
+    return t.data_ptr()
+
+
+launch_count = 0  # number of library kernels launched by this process (bench.py reports it)
+
+
+def _launched(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, *, M: Optional[int] = None,
+         lda: Optional[int] = None, a_rows: Optional[int] = None, taps: int = 1, tap_k: int = 0,
+         tap_row_shift: int = 0, K: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual; bf16 operands -> tcgen05, f32 -> FFMA.
+
+    `a` may be any tensor whose storage holds the rows (lda/a_rows/M override the 2-D view for implicit
+    convolutions); `out`/`residual` are 2-D with unit inner stride."""
+    lib = require_device()
+    assert a.dtype == w.dtype and w.dim() == 2 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
+    N = w.shape[0]
+    Kk = K if K is not None else w.shape[1]
+    g = GemmArgs()
+    g.A, g.W, g.C = _ptr(a), _ptr(w), _ptr(out)
+    g.lda = lda if lda is not None else a.stride(0)
+    g.M = M if M is not None else a.shape[0]
+    g.a_rows = a_rows if a_rows is not None else (a.shape[0] if a.dim() == 2 else g.M)
+    g.ldw = w.stride(0)
+    g.bias = _ptr(bias)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    g.residual = _ptr(residual)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.res_dtype = _dt(residual) if residual is not None else F32
+    g.out_dtype = _dt(out)
+    g.ldc = out.stride(0)
+    g.N, g.K = N, Kk
+    g.act, g.taps, g.tap_k, g.tap_row_shift = act, taps, tap_k, tap_row_shift
+    assert out.shape[0] >= g.M and out.shape[1] == N
+    fn = lib.fdm_gemm_bf16 if a.dtype == torch.bfloat16 else lib.fdm_gemm_f32
+    _check(fn(C.byref(g), _stream()))
+    _launched()
+    return out
+
+
+def layernorm(x: torch.Tensor, out: torch.Tensor, g1=None, b1=None, r1=None, act1: int = ACT_NONE, r2=None,
+              vec2=None, vec_index_dev=None, g2=None, b2=None, out2=None, eps: float = 1e-5) -> torch.Tensor:
+    lib = require_device()
+    n = NormArgs()
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d) if x.is_contiguous() else x
+    assert x2.dim() == 2 and x2.stride(1) == 1
+    n.x, n.ldx, n.x_dtype = _ptr(x2), x2.stride(0), _dt(x2)
+
+    def two_d(t):
+        t2 = t.reshape(-1, d) if t.is_contiguous() else t
+        assert t2.dim() == 2 and t2.stride(1) == 1 and t2.shape[0] >= x2.shape[0]
+        return t2
+
+    if r1 is not None:
+        r = two_d(r1); n.r1, n.ldr1, n.r1_dtype = _ptr(r), r.stride(0), _dt(r)
+    if r2 is not None:
+        r = two_d(r2); n.r2, n.ldr2, n.r2_dtype = _ptr(r), r.stride(0), _dt(r)
+    n.g1, n.b1, n.g2, n.b2 = _ptr(g1), _ptr(b1), _ptr(g2), _ptr(b2)
+    n.act1 = act1
+    n.vec2, n.vec_index_dev = _ptr(vec2), _ptr(vec_index_dev)
+    o = two_d(out); n.out, n.ldo, n.out_dtype = _ptr(o), o.stride(0), _dt(o)
+    if out2 is not None:
+        o2 = two_d(out2); n.out2, n.ldo2, n.out2_dtype = _ptr(o2), o2.stride(0), _dt(o2)
+    n.rows, n.d, n.eps = x2.shape[0], d, eps
+    _check(lib.fdm_layernorm(C.byref(n), _stream()))
+    _launched()
+    return out
+
+
+def leaky_instnorm(x: torch.Tensor, out: torch.Tensor, B: int, T: int, t_stride: int, Cn: int,
+                   slope: float = 0.2, eps: float = 1e-5) -> torch.Tensor:
+    lib = require_device()
+    _check(lib.fdm_leaky_instnorm(_ptr(x), _dt(x), _ptr(out), _dt(out), B, T, t_stride, Cn, slope, eps, _stream()))
+    _launched()
+    return out
+
+
+def self_attention(q, k, v, out, B: int, T: int, t_stride: int, H: int, dh: int, scale: float,
+                   slopes: Optional[torch.Tensor] = None, period: int = 0) -> torch.Tensor:
+    """q/k/v/out: 2-D row views (row = b*t_stride + t) whose column 0 is head 0 of the respective operand."""
+    lib = require_device()
+    a = AttnArgs()
+    a.Q, a.K, a.V, a.O = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.dtype = _dt(q)
+    assert q.dtype == k.dtype == v.dtype == out.dtype
+    a.B, a.T, a.t_stride, a.H, a.dh, a.scale = B, T, t_stride, H, dh, scale
+    a.bias_mode = 1 if slopes is not None else 0
+    a.period = period
+    a.slopes = _ptr(slopes)
+    _check(lib.fdm_self_attention(C.byref(a), _stream()))
+    _launched()
+    return out
+
+
+def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: float = 0.0, noise=None,
+              out_bf16=None, t_per_clip=None, t_sched=None, cursor=None, seed: int = 0,
+              clip_index0: int = 0) -> torch.Tensor:
+    lib = require_device()
+    a = DdpmArgs()
+    B = x_t.shape[0]
+    for t in (x0_cond, x_t, out, x0_uncond, noise):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x_t.numel())
+    a.x0_cond, a.x0_uncond, a.guidance = _ptr(x0_cond), _ptr(x0_uncond), guidance
+    a.x_t, a.noise, a.out, a.out_bf16 = _ptr(x_t), _ptr(noise), _ptr(out), _ptr(out_bf16)
+    a.c1, a.c2, a.sigma = _ptr(c1), _ptr(c2), _ptr(sigma)
+    if t_per_clip is not None:
+        assert t_per_clip.dtype == torch.int64 and t_per_clip.numel() == B
+    a.t_per_clip, a.t_sched, a.cursor_dev = _ptr(t_per_clip), _ptr(t_sched), _ptr(cursor)
+    a.B, a.elems_per_clip = B, x_t.numel() // B
+    a.seed, a.clip_index0 = seed, clip_index0
+    _check(lib.fdm_ddpm_step(C.byref(a), _stream()))
+    _launched()
+    return out
+
+
+def advance_cursor(cursor: torch.Tensor) -> None:
+    _check(require_device().fdm_advance_cursor(_ptr(cursor), _stream()))
+    _launched()
+
+
+def philox_normal(out: torch.Tensor, seed: int, clip_index0: int, t: int) -> torch.Tensor:
+    B = out.shape[0]
+    _check(require_device().fdm_philox_normal(_ptr(out), B, out.numel() // B, seed, clip_index0, t, _stream()))
+    _launched()
+    return out
+
+
+def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, n_codes: int, code_offset=None, want_bdl=True,
+                want_rows=False):
+    """z (B, L, D) f32 -> (indices (B*L, 1) int64, z_q (B, D, L) or None, z_q rows (B, L, D) or None)."""
+    lib = require_device()
+    assert z.dtype == torch.float32 and z.is_contiguous() and codebook.dtype == torch.float32 and codebook.is_contiguous()
+    B, L, D = z.shape
+    idx = torch.empty((B * L, 1), dtype=torch.int64, device=z.device)
+    zq = torch.empty((B, D, L), dtype=torch.float32, device=z.device) if want_bdl else None
+    zr = torch.empty((B, L, D), dtype=torch.float32, device=z.device) if want_rows else None
+    if code_offset is not None:
+        assert code_offset.dtype == torch.int64 and code_offset.numel() == B
+    _check(lib.fdm_vq_quantize(_ptr(z), _ptr(codebook), _ptr(code_offset), B, L, D, n_codes, _ptr(idx), _ptr(zq),
+                               _ptr(zr), _stream()))
+    _launched()
+    return idx, zq, zr
+
+
+def cast(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    _check(require_device().fdm_cast(_ptr(src), _dt(src), _ptr(dst), _dt(dst), src.numel(), _stream()))
+    _launched()
+    return dst
+
+
+def transpose_bcl_to_blc(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    B, Cn, L = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous() and dst.numel() == src.numel()
+    _check(require_device().fdm_transpose_bcl_to_blc(_ptr(src), _ptr(dst), _dt(dst), B, Cn, L, _stream()))
+    _launched()
+    return dst
+
+
+def pad_time(src: torch.Tensor, dst: torch.Tensor, B: int, T: int, Cn: int, pad_l: int, pad_r: int, mode: int,
+             src_t_stride: Optional[int] = None) -> torch.Tensor:
+    assert src.dtype == dst.dtype and dst.numel() >= B * (pad_l + T + pad_r) * Cn
+    _check(require_device().fdm_pad_time(_ptr(src), src_t_stride or T, _ptr(dst), _dt(src), B, T, Cn, pad_l, pad_r,
+                                         mode, _stream()))
+    _launched()
+    return dst
+
+
+def hubert_conv0(audio, w, bias, ln_g, ln_b, out, Lout: int, out_t_stride: int, Cn: int) -> torch.Tensor:
+    B, L = audio.shape
+    assert audio.dtype == torch.float32 and audio.is_contiguous()
+    _check(require_device().fdm_hubert_conv0(_ptr(audio), B, L, _ptr(w), _ptr(bias), _ptr(ln_g), _ptr(ln_b),
+                                             _ptr(out), _dt(out), Lout, out_t_stride, Cn, _stream()))
+    _launched()
+    return out

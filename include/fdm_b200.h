@@ -1,0 +1,181 @@
+/*
+ * fdm_b200.h — C ABI of libfdm_b200.so: the sm_100a kernels behind the LG-LDM sampling hot path
+ * of wangxuanx/Face-Diffusion-Model.
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + explicit sizes/strides (element units unless stated), no torch types;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every call is asynchronous on `stream`, never allocates or frees caller memory;
+ *   - return 0 on success, non-zero on error; fdm_last_error() returns a thread-local message;
+ *   - dtype codes: FDM_F32 = 0, FDM_BF16 = 1.
+ *
+ * The reference has no FFI layer (it is pure PyTorch); each entry point cites the reference
+ * Python call site it replaces (paths relative to the reference checkout).
+ */
+#ifndef FDM_B200_H
+#define FDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDM_F32 0
+#define FDM_BF16 1
+
+/* activation codes for the GEMM / norm epilogues */
+#define FDM_ACT_NONE 0
+#define FDM_ACT_RELU 1       /* nn.TransformerDecoderLayer FFN (models/fdm_vocaset.py:45) */
+#define FDM_ACT_MISH 2       /* nn.Mish in audio_extract / latent_encoder / time_embedd (models/fdm_vocaset.py:20-39) */
+#define FDM_ACT_GELU_ERF 3   /* HF HuBERT "gelu" (transformers/models/hubert/modeling_hubert.py) */
+#define FDM_ACT_GELU_TANH 4  /* models/utils/base_model_util.py:81-94 */
+#define FDM_ACT_LEAKY02 5    /* nn.LeakyReLU(0.2) in the VQ decoder expander (models/vq_vae_vocaset.py:197) */
+
+/* ---- library / device ------------------------------------------------------------------- */
+const char* fdm_last_error(void);
+/* Fills SM count and compute capability of the current device; fails unless it is sm_100. */
+int fdm_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+int fdm_abi_version(void);
+
+/* ---- dense layers ----------------------------------------------------------- *
+ * C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) + residual[M,N]
+ * replaces every nn.Linear / Conv1d call on the path (models/fdm_vocaset.py:20-51,
+ * models/lib/base_models.py:71-174, models/vq_vae_vocaset.py:194-258, HF HuBERT convs/linears).
+ *
+ * Implicit 1-D convolution: with taps > 1, K = taps * tap_k and
+ *   A(m, tap*tap_k + c) = A[(m + tap*tap_row_shift) * lda + c],
+ * i.e. the k-th filter tap reads the activation row shifted by tap*tap_row_shift; strided convs
+ * use a plain GEMM with lda = stride * C_in (rows overlap). a_rows = number of addressable rows
+ * of A (bounds for the TMA descriptor; >= M + (taps-1)*tap_row_shift).
+ */
+typedef struct fdm_gemm_args {
+  const void* A;          /* bf16 (fdm_gemm_bf16) or f32 (fdm_gemm_f32), row-major, K contiguous */
+  int64_t lda;            /* row stride of A in elements */
+  int64_t a_rows;
+  const void* W;          /* same dtype as A, [N, K] row-major (nn.Linear.weight layout) */
+  int64_t ldw;
+  const float* bias;      /* [N] f32 or NULL */
+  const void* residual;   /* [M, N] or NULL; added after the activation */
+  int64_t ldr;
+  int32_t res_dtype;      /* FDM_F32 / FDM_BF16 */
+  int32_t out_dtype;      /* FDM_F32 / FDM_BF16 */
+  void* C;
+  int64_t ldc;
+  int64_t M, N, K;
+  int32_t act;
+  int32_t taps;           /* 1 = plain GEMM */
+  int64_t tap_k;
+  int64_t tap_row_shift;
+} fdm_gemm_args;
+
+/* TMA-fed tcgen05/TMEM GEMM, bf16 operands, fp32 accumulation. */
+int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream);
+/* fp32 FFMA GEMM (deterministic k order) — the "fp32 mode" used for the 1e-4 parity runs. */
+int fdm_gemm_f32(const fdm_gemm_args* args, void* stream);
+
+/* ---- normalisation ------------------------------------------------------- *
+ * Row LayerNorm with fused residual adds; replaces norm1/2/3 of nn.TransformerDecoderLayer
+ * (post-norm, eps 1e-5), base_models.Norm (models/lib/base_models.py:37-52) and HF HuBERT LNs.
+ *   y = x + r1 (if r1)            ; y = LN(y; g1, b1)  (if g1)  ; y = act1(y)
+ *   if g2: y = y + r2 (if r2) + vec2[vec_index * d .. ] (if vec2) ; y = LN(y; g2, b2)
+ * out (out_dtype) and optional out2 (the other dtype) receive y.
+ * vec_index is read on the device from *vec_index_dev (the denoising step t) when vec2 != NULL.
+ */
+typedef struct fdm_norm_args {
+  const void* x; int64_t ldx; int32_t x_dtype;
+  const void* r1; int64_t ldr1; int32_t r1_dtype;
+  const float* g1; const float* b1;
+  int32_t act1;
+  const void* r2; int64_t ldr2; int32_t r2_dtype;
+  const float* vec2; const int32_t* vec_index_dev;
+  const float* g2; const float* b2;
+  void* out; int64_t ldo; int32_t out_dtype;
+  void* out2; int64_t ldo2; int32_t out2_dtype;
+  int64_t rows; int64_t d;
+  float eps;
+} fdm_norm_args;
+int fdm_layernorm(const fdm_norm_args* args, void* stream);
+
+/* LeakyReLU(0.2) + InstanceNorm1d over time (affine=False, eps, biased variance) on a
+ * [B, T(ld rows per clip = t_stride), C] activation; models/vq_vae_vocaset.py:194-199. */
+int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int32_t out_dtype,
+                       int64_t B, int64_t T, int64_t t_stride, int64_t C, float slope, float eps,
+                       void* stream);
+
+/* ---- attention ---------------------------------------------------------------- *
+ * O[b,t,h,:] = softmax_j( scale * Q[b,t,h,:].K[b,j,h,:] + bias(h,t,j) ) V[b,j,h,:]
+ * bias_mode 0: none (VQ decoder, models/lib/base_models.py:150-174; HuBERT encoder)
+ * bias_mode 1: FaceFormer-style periodic ALiBi + causal mask computed in-kernel,
+ *              bias = -slopes[h] * floor((t-j)/period) for j<=t, -inf for j>t
+ *              (models/fdm_vocaset.py:94-115 init_biased_mask; never materialised here).
+ * Row of (b,t) = b*t_stride + t; head h at column h*dh of each of Q/K/V; ld* in elements.
+ */
+typedef struct fdm_attn_args {
+  const void* Q; const void* K; const void* V; int64_t ldq; int64_t ldk; int64_t ldv;
+  void* O; int64_t ldo;
+  int32_t dtype;          /* dtype of Q/K/V/O */
+  int64_t B, T, t_stride, H, dh;
+  float scale;
+  int32_t bias_mode; int32_t period; const float* slopes;
+} fdm_attn_args;
+int fdm_self_attention(const fdm_attn_args* args, void* stream);
+
+/* ---- diffusion step (S4 + S5 + C1) --------------------------------------------- *
+ * One fused, vectorised kernel per denoising step:
+ *   x0   = x0_uncond + guidance * (x0_cond - x0_uncond)      (utiles/classifierfree.py:20-21; skipped if x0_uncond == NULL)
+ *   mean = c1[t]*x0 + c2[t]*x_t                              (diffusion_BIWI_encoder_decoder.py:632-639)
+ *   out  = mean + sigma[t]*noise   (no noise when t == 0)    (diffusion_BIWI_encoder_decoder.py:650-656)
+ * t comes from t_per_clip[b] (int64, p_sample API) or, if NULL, from t_sched[*cursor_dev]
+ * (CUDA-graph replay without host sync). noise == NULL selects the in-kernel Philox4x32-10 +
+ * Box-Muller generator keyed by (seed, clip_index0 + b, t, element). Products and sums are
+ * individually rounded (no FMA contraction) to match the PyTorch expression bit for bit.
+ * out_bf16 (optional) receives a bf16 copy of out for the next step's first GEMM.
+ */
+typedef struct fdm_ddpm_args {
+  const float* x0_cond; const float* x0_uncond; float guidance;
+  const float* x_t; const float* noise;
+  float* out; void* out_bf16;
+  const float* c1; const float* c2; const float* sigma;    /* [num_timesteps] tables */
+  const int64_t* t_per_clip; const int32_t* t_sched; const int32_t* cursor_dev;
+  int64_t B; int64_t elems_per_clip;
+  uint64_t seed; int64_t clip_index0;
+} fdm_ddpm_args;
+int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream);
+/* cursor_dev[0] += 1 (end of a graph-replayed step). */
+int fdm_advance_cursor(int32_t* cursor_dev, void* stream);
+/* Fill out[B*elems_per_clip] with the same Philox normals the fused step would draw for step t. */
+int fdm_philox_normal(float* out, int64_t B, int64_t elems_per_clip, uint64_t seed,
+                      int64_t clip_index0, int32_t t, void* stream);
+
+/* ---- VQ quantiser --------------------------------------------------------- *
+ * For each row z (D floats): d_j = (sum z^2 + sum e_j^2) - 2*(z . e_j), all fp32, each sum a
+ * sequential fmaf chain over k = 0..D-1 starting from 0.0f; index = argmin_j d_j, lowest j on
+ * ties (models/lib/quantizer.py:35-64, models/vq_vae_emotion.py:221-252).
+ * code_offset[b] (optional) selects the per-clip codebook slice [off, off+n_codes) (emotion).
+ * Writes indices (int64, local to the slice) and z_q in the reference's permuted layout
+ * z_q[b, k, l] (B, D, L) and/or row layout z_q_rows[b, l, k].
+ */
+int fdm_vq_quantize(const float* z, const float* codebook, const int64_t* code_offset,
+                    int64_t B, int64_t L, int64_t D, int64_t n_codes,
+                    int64_t* indices, float* zq_bdl, float* zq_rows, void* stream);
+
+/* ---- small data-movement kernels ------------------------------------------------------------ */
+int fdm_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+/* dst[b, l, c] = src[b, c, l] (+ cast); used for VQAutoEncoder.decode's (B,D,L) input. */
+int fdm_transpose_bcl_to_blc(const float* src, void* dst, int32_t dst_dtype,
+                             int64_t B, int64_t C, int64_t L, void* stream);
+/* Copy [B, T, C] rows into a per-clip padded buffer [B, pad_l + T + pad_r, C]; padding rows are
+ * replicated edge rows (mode 1, Conv1d padding_mode='replicate') or zeros (mode 0). */
+int fdm_pad_time(const void* src, int64_t src_t_stride, void* dst, int32_t dtype, int64_t B, int64_t T,
+                 int64_t C, int64_t pad_l, int64_t pad_r, int32_t mode, void* stream);
+/* HuBERT conv layer 0: Conv1d(1, C, k=10, stride=5, bias) + LayerNorm(C) + GELU on raw audio.
+ * audio [B, L] f32 -> out [B, out_t_stride, C] (rows >= Lout zero-filled). */
+int fdm_hubert_conv0(const float* audio, int64_t B, int64_t L, const float* w, const float* bias,
+                     const float* ln_g, const float* ln_b, void* out, int32_t out_dtype,
+                     int64_t Lout, int64_t out_t_stride, int64_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDM_B200_H */

@@ -1,0 +1,266 @@
+"""Per-kernel numerics: each C-ABI kernel against a plain PyTorch fp32 reference of the same op (GPU)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+GEMM_SHAPES = [
+    # M, N, K
+    (128, 256, 64), (256, 256, 128), (200, 1024, 1024), (198, 3072, 1024), (792, 1024, 2048),
+    (1000, 512, 512), (130, 64, 64), (257, 192, 320), (12672, 1024, 1024), (333, 15069, 1024),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_bf16_tcgen05(cuda_dev, M, N, K, out_dtype):
+    from fdm_b200 import lib
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    out = torch.full((M, N), float("nan"), device=cuda_dev, dtype=out_dtype)
+    lib.gemm(a, w, out, bias=bias)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 2e-5
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < tol
+    err = (out.float() - ref).abs().max().item()
+    assert err < (0.1 if out_dtype == torch.bfloat16 else 1e-3), err
+
+
+@pytest.mark.parametrize("act", [1, 2, 3, 4, 5])
+def test_gemm_bf16_epilogue(cuda_dev, act):
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    M, N, K = 300, 1024, 512
+    g = torch.Generator(device="cpu").manual_seed(act)
+    a = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    fns = {1: F.relu, 2: F.mish, 3: F.gelu, 4: lambda x: F.gelu(x, approximate="tanh"), 5: lambda x: F.leaky_relu(x, 0.2)}
+    ref = fns[act](a.float() @ w.float().t() + bias) + res
+    for res_t in (res, res.bfloat16()):
+        out = torch.empty(M, N, device=cuda_dev)
+        lib.gemm(a, w, out, bias=bias, act=act, residual=res_t)
+        torch.cuda.synchronize()
+        assert _rel(out, fns[act](a.float() @ w.float().t() + bias) + res_t.float()) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_implicit_conv(cuda_dev, dtype):
+    """Conv1d(k=5, pad=2 replicate) and a stride-2 k=3 conv as shifted-row / overlapping-row GEMMs."""
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    B, T, Cin, Cout = 3, 50, 128, 192
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(B, T, Cin, generator=g).to(cuda_dev)
+    wt = (torch.randn(Cout, Cin, 5, generator=g) / math.sqrt(5 * Cin)).to(cuda_dev)
+    bias = torch.randn(Cout, generator=g).to(cuda_dev)
+    if dtype == torch.bfloat16:
+        x, wt = x.bfloat16().float(), wt.bfloat16().float()
+    ref = F.conv1d(F.pad(x.double().transpose(1, 2), (2, 2), mode="replicate"), wt.double(), bias.double()).transpose(1, 2).float()
+    xp = torch.empty(B, T + 4, Cin, device=cuda_dev, dtype=dtype)
+    lib.pad_time(x.to(dtype).contiguous(), xp, B, T, Cin, 2, 2, 1)
+    wk = wt.permute(0, 2, 1).reshape(Cout, 5 * Cin).contiguous().to(dtype)  # [Cout, tap, Cin]
+    out = torch.zeros(B * (T + 4), Cout, device=cuda_dev)
+    lib.gemm(xp, wk, out, bias=bias, M=B * (T + 4) - 4, lda=Cin, a_rows=B * (T + 4), taps=5, tap_k=Cin, tap_row_shift=1)
+    torch.cuda.synchronize()
+    got = out.view(B, T + 4, Cout)[:, :T]
+    assert _rel(got, ref) < (2e-5 if dtype == torch.float32 else 1e-4)
+
+    # stride-2, k=3, no padding: rows overlap (lda = 2*Cin, K = 3*Cin)
+    Lin = 64
+    x2 = torch.randn(B, Lin, Cin, generator=g).to(cuda_dev)
+    w2 = (torch.randn(Cout, Cin, 3, generator=g) / math.sqrt(3 * Cin)).to(cuda_dev)
+    if dtype == torch.bfloat16:
+        x2, w2 = x2.bfloat16().float(), w2.bfloat16().float()
+    ref2 = F.conv1d(x2.double().transpose(1, 2), w2.double(), None, stride=2).transpose(1, 2).float()  # B, 31, Cout
+    Lout = (Lin - 3) // 2 + 1
+    w2k = w2.permute(0, 2, 1).reshape(Cout, 3 * Cin).contiguous().to(dtype)
+    xin = torch.zeros(B * Lin + 2, Cin, device=cuda_dev, dtype=dtype)  # 2 slack rows for the last window
+    xin[:B * Lin] = x2.reshape(B * Lin, Cin).to(dtype)
+    out2 = torch.zeros(B * Lin // 2, Cout, device=cuda_dev)
+    lib.gemm(xin, w2k, out2, M=B * Lin // 2, lda=2 * Cin, a_rows=B * Lin // 2, K=3 * Cin)
+    torch.cuda.synchronize()
+    got2 = out2.view(B, Lin // 2, Cout)[:, :Lout]
+    assert _rel(got2, ref2) < (2e-5 if dtype == torch.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(198, 1024, 1024), (77, 130, 50), (512, 15069, 64), (300, 64, 2048)])
+def test_gemm_f32(cuda_dev, M, N, K):
+    from fdm_b200 import lib
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    out = torch.empty(M, N, device=cuda_dev)
+    lib.gemm(a, w, out, bias=bias, act=lib.ACT_MISH)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.mish((a.double() @ w.double().t() + bias.double())).float()
+    assert _rel(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("d", [512, 1024, 64])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_fused(cuda_dev, d, dtype):
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    rows = 333
+    g = torch.Generator(device="cpu").manual_seed(d)
+    mk = lambda *s: torch.randn(*s, generator=g).to(cuda_dev)
+    x, r1, r2 = mk(rows, d).to(dtype), mk(rows, d).to(dtype), mk(rows, d)
+    g1, b1, g2, b2 = mk(d), mk(d), mk(d), mk(d)
+    vec = mk(10, d)
+    idx = torch.tensor([7], dtype=torch.int32, device=cuda_dev)
+    out = torch.empty(rows, d, device=cuda_dev, dtype=dtype)
+    out2 = torch.empty(rows, d, device=cuda_dev, dtype=torch.float32 if dtype == torch.bfloat16 else torch.bfloat16)
+    lib.layernorm(x, out, g1=g1, b1=b1, r1=r1, r2=r2, vec2=vec, vec_index_dev=idx, g2=g2, b2=b2, out2=out2)
+    torch.cuda.synchronize()
+    y = F.layer_norm(x.float() + r1.float(), (d,), g1, b1)
+    ref = F.layer_norm(y + r2 + vec[7], (d,), g2, b2)
+    tol = 1e-5 if dtype == torch.float32 else 5e-3
+    assert _rel(out, ref) < tol
+    assert _rel(out2, ref) < 5e-3
+    # single LN + GELU (HuBERT conv stack)
+    o3 = torch.empty(rows, d, device=cuda_dev, dtype=dtype)
+    lib.layernorm(x, o3, g1=g1, b1=b1, act1=lib.ACT_GELU_ERF)
+    assert _rel(o3, F.gelu(F.layer_norm(x.float(), (d,), g1, b1))) < tol
+
+
+def _alibi_mask(H, T, period):
+    # closed form of models/fdm_vocaset.py:94-115
+    slopes = torch.tensor([2.0 ** (-(2.0 ** -(math.log2(H) - 3)) * (i + 1)) for i in range(H)])
+    i = torch.arange(T)[:, None]
+    j = torch.arange(T)[None, :]
+    bias = -((i - j) // period).float()
+    m = slopes[:, None, None] * bias[None]
+    m = m.masked_fill((j > i)[None], float("-inf"))
+    return slopes, m
+
+
+@pytest.mark.parametrize("H,dh,T,causal", [(8, 128, 198, True), (4, 128, 99, True), (4, 256, 149, True),
+                                            (8, 128, 70, False), (16, 64, 198, False)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention(cuda_dev, H, dh, T, causal, dtype):
+    from fdm_b200 import lib
+    B, d = 3, H * dh
+    t_stride = T + 5
+    g = torch.Generator(device="cpu").manual_seed(T)
+    qkv = torch.randn(B, t_stride, 3 * d, generator=g).to(cuda_dev).to(dtype)
+    out = torch.zeros(B * t_stride, d, device=cuda_dev, dtype=dtype)
+    rows = qkv.view(B * t_stride, 3 * d)
+    slopes = None
+    scale = 1.0 / math.sqrt(dh)
+    bias = torch.zeros(H, T, T)
+    if causal:
+        slopes, bias = _alibi_mask(H, T, 30)
+        slopes = slopes.to(cuda_dev)
+    lib.self_attention(rows[:, 0:], rows[:, d:], rows[:, 2 * d:], out, B, T, t_stride, H, dh, scale, slopes=slopes, period=30)
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, t_stride, H, dh)[:, :T].permute(0, 2, 1, 3) for t in qkv.split(d, dim=-1)]
+    s = (q @ k.transpose(-1, -2)) * scale + bias.to(cuda_dev)
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
+    got = out.view(B, t_stride, d)[:, :T]
+    assert _rel(got, ref) < (2e-5 if dtype == torch.float32 else 1e-2)
+
+
+def test_ddpm_step_bit_exact(cuda_dev):
+    from fdm_b200 import lib
+    B, n = 4, 3168 * 64
+    g = torch.Generator(device="cpu").manual_seed(0)
+    mk = lambda: torch.randn(B, n, generator=g).to(cuda_dev)
+    c, u, xt, nz = mk(), mk(), mk(), mk()
+    tabs = [torch.rand(1000, generator=g).to(cuda_dev) for _ in range(3)]
+    t = torch.tensor([999, 500, 1, 0], device=cuda_dev)
+    out = torch.empty_like(xt)
+    ob = torch.empty(B, n, device=cuda_dev, dtype=torch.bfloat16)
+    lib.ddpm_step(c, xt, out, *tabs, x0_uncond=u, guidance=2.5, noise=nz, out_bf16=ob, t_per_clip=t)
+    torch.cuda.synchronize()
+    x0 = u + 2.5 * (c - u)
+    e = lambda tab: tab[t][:, None]
+    ref = e(tabs[0]) * x0 + e(tabs[1]) * xt + e(tabs[2]) * nz * (t > 0)[:, None]
+    assert torch.equal(out, ref)
+    assert torch.equal(ob, ref.bfloat16())
+    # graph-style addressing: t from t_sched[*cursor]
+    sched = torch.arange(999, -1, -1, dtype=torch.int32, device=cuda_dev)
+    cur = torch.tensor([499], dtype=torch.int32, device=cuda_dev)
+    lib.ddpm_step(c, xt, out, *tabs, noise=nz, t_sched=sched, cursor=cur)
+    lib.advance_cursor(cur)
+    torch.cuda.synchronize()
+    assert cur.item() == 500
+    assert torch.equal(out, tabs[0][500] * c + tabs[1][500] * xt + tabs[2][500] * nz)
+
+
+def test_philox_normal_stats(cuda_dev):
+    from fdm_b200 import lib
+    out = torch.empty(8, 1 << 18, device=cuda_dev)
+    lib.philox_normal(out, seed=1234, clip_index0=3, t=17)
+    o2 = torch.empty(4, 1 << 18, device=cuda_dev)
+    lib.philox_normal(o2, seed=1234, clip_index0=5, t=17)
+    torch.cuda.synchronize()
+    assert abs(out.mean().item()) < 5e-3 and abs(out.std().item() - 1) < 5e-3
+    assert torch.equal(out[2:6], o2)  # keyed by global clip index: invariant to sharding
+    assert not torch.equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("D,L", [(64, 3168), (128, 1192), (64, 100)])
+def test_vq_quantize(cuda_dev, D, L):
+    from fdm_b200 import lib
+    B, n = 3, 256
+    g = torch.Generator(device="cpu").manual_seed(D + L)
+    z = torch.randn(B, L, D, generator=g).to(cuda_dev)
+    cb = torch.randn(7 * n, D, generator=g).to(cuda_dev)
+    off = torch.tensor([0, 256 * 3, 256 * 6], device=cuda_dev)
+    idx, zq, zr = lib.vq_quantize(z, cb, n, code_offset=off, want_rows=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        e = cb[off[b]:off[b] + n].double()
+        d = (z[b].double() ** 2).sum(1, keepdim=True) + (e ** 2).sum(1) - 2 * z[b].double() @ e.t()
+        ref = d.argmin(1)
+        got = idx.view(B, L)[b]
+        # fp32 vs fp64 argmin may differ only on near-ties
+        bad = (got != ref)
+        if bad.any():
+            dd = d[bad]
+            gap = (dd.gather(1, got[bad][:, None]) - dd.min(1, keepdim=True).values).abs().max().item()
+            assert gap < 1e-4, gap
+        assert torch.equal(zr[b], cb[off[b] + got])
+        assert torch.equal(zq[b], zr[b].t())
+    assert idx.min() >= 0 and idx.max() < n
+
+
+def test_misc_kernels(cuda_dev):
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(1)
+    src = torch.randn(2, 70, 45, generator=g).to(cuda_dev)
+    dst = torch.empty(2, 45, 70, device=cuda_dev, dtype=torch.bfloat16)
+    lib.transpose_bcl_to_blc(src, dst)
+    assert torch.equal(dst, src.transpose(1, 2).bfloat16())
+    # LeakyReLU + InstanceNorm over time
+    x = torch.randn(3, 50, 96, generator=g).to(cuda_dev)
+    o = torch.empty_like(x)
+    lib.leaky_instnorm(x, o, 3, 50, 50, 96)
+    ref = F.instance_norm(F.leaky_relu(x, 0.2).transpose(1, 2)).transpose(1, 2)
+    assert _rel(o, ref) < 1e-5
+    # HuBERT conv0 + LN + GELU
+    audio = torch.randn(2, 4000, generator=g).to(cuda_dev)
+    w, b = torch.randn(512, 1, 10, generator=g).to(cuda_dev), torch.randn(512, generator=g).to(cuda_dev)
+    lg, lb = torch.randn(512, generator=g).to(cuda_dev), torch.randn(512, generator=g).to(cuda_dev)
+    Lout = (4000 - 10) // 5 + 1
+    out = torch.empty(2, 800, 512, device=cuda_dev)
+    lib.hubert_conv0(audio, w.view(512, 10).contiguous(), b, lg, lb, out, Lout, 800, 512)
+    ref = F.gelu(F.layer_norm(F.conv1d(audio[:, None], w, b, stride=5).transpose(1, 2), (512,), lg, lb))
+    torch.cuda.synchronize()
+    assert _rel(out[:, :Lout], ref) < 1e-5
+    assert (out[:, Lout:] == 0).all()
