@@ -46,7 +46,7 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t clip, u
 }
 
 __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, const int64_t n4, const int64_t e4_per_clip) {
-  const int t_graph = a.t_per_clip ? 0 : a.t_sched[*a.cursor_dev];
+  const int t_graph = a.t_per_clip ? 0 : *a.t_dev;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t b = i / e4_per_clip;
@@ -88,7 +88,11 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, c
   }
 }
 
-__global__ void advance_cursor_kernel(int32_t* cursor) { *cursor += 1; }
+__global__ void advance_cursor_kernel(int32_t* cursor, const int32_t* sched, int n, int32_t* t_dev) {
+  const int c = *cursor + 1;
+  *cursor = c;
+  *t_dev = sched[c < n ? c : n - 1];
+}
 
 __global__ void __launch_bounds__(256) philox_fill_kernel(float* out, int64_t n4, int64_t e4_per_clip, uint64_t seed,
                                                           int64_t clip0, int t) {
@@ -112,7 +116,7 @@ extern "C" int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream) {
   FDM_CHECK_ARG(args != nullptr, "fdm_ddpm_step: null args");
   const fdm_ddpm_args& a = *args;
   FDM_CHECK_ARG(a.x0_cond && a.x_t && a.out && a.c1 && a.c2 && a.sigma, "fdm_ddpm_step: null operand");
-  FDM_CHECK_ARG(a.t_per_clip || (a.t_sched && a.cursor_dev), "fdm_ddpm_step: need t_per_clip or (t_sched, cursor_dev)");
+  FDM_CHECK_ARG(a.t_per_clip || a.t_dev, "fdm_ddpm_step: need t_per_clip or t_dev");
   FDM_CHECK_ARG(a.B > 0 && a.elems_per_clip > 0 && a.elems_per_clip % 4 == 0, "fdm_ddpm_step: elems_per_clip must be a positive multiple of 4");
   const uintptr_t al = reinterpret_cast<uintptr_t>(a.x0_cond) | reinterpret_cast<uintptr_t>(a.x0_uncond) |
                        reinterpret_cast<uintptr_t>(a.x_t) | reinterpret_cast<uintptr_t>(a.noise) |
@@ -124,9 +128,9 @@ extern "C" int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream) {
   return 0;
 }
 
-extern "C" int fdm_advance_cursor(int32_t* cursor_dev, void* stream) {
-  FDM_CHECK_ARG(cursor_dev != nullptr, "fdm_advance_cursor: null cursor");
-  advance_cursor_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cursor_dev);
+extern "C" int fdm_advance_cursor(int32_t* cursor_dev, const int32_t* t_sched, int32_t n_sched, int32_t* t_dev, void* stream) {
+  FDM_CHECK_ARG(cursor_dev && t_sched && t_dev && n_sched > 0, "fdm_advance_cursor: bad arguments");
+  advance_cursor_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cursor_dev, t_sched, n_sched, t_dev);
   FDM_CHECK_LAUNCH();
   return 0;
 }

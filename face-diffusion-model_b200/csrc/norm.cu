@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const fdm_norm_args a) {
       const int c0 = (i * 32 + lane) * 4;
       if (i < nv && c0 < d) {
         if (a.r2) {
-          const float4 r = load4(a.r2, a.r2_dtype, row * a.ldr2 + c0);
+          const float4 r = load4(a.r2, a.r2_dtype, (a.r2_rows > 0 ? row % a.r2_rows : row) * a.ldr2 + c0);
           v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
         }
         if (vec) {
@@ -112,11 +112,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const fdm_norm_args a) {
 
 // block = 32 channels x 8 time-lanes; grid = (C/32, B)
 __global__ void __launch_bounds__(256) leaky_instnorm_kernel(const void* x, int x_dtype, void* out, int out_dtype, int T,
-                                                             int64_t t_stride, int C, float slope, float eps) {
+                                                             int64_t t_stride, int64_t out_t_stride, int C, float slope,
+                                                             float eps) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const int64_t base = static_cast<int64_t>(blockIdx.y) * t_stride * C;
+  const int64_t obase = static_cast<int64_t>(blockIdx.y) * out_t_stride * C;
   const bool ok = c < C;
   float s = 0.f;
   for (int t = ty; t < T; t += 8)
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256) leaky_instnorm_kernel(const void* x, int 
     if (ok) {
       float v = ld_as_float(x, x_dtype, base + static_cast<int64_t>(t) * C + c);
       v = (v > 0.f ? v : slope * v);
-      st_from_float(out, out_dtype, base + static_cast<int64_t>(t) * C + c, (v - mean) * rstd);
+      st_from_float(out, out_dtype, obase + static_cast<int64_t>(t) * C + c, (v - mean) * rstd);
     }
 }
 
@@ -178,11 +180,12 @@ extern "C" int fdm_layernorm(const fdm_norm_args* args, void* stream) {
 }
 
 extern "C" int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int32_t out_dtype, int64_t B, int64_t T,
-                                  int64_t t_stride, int64_t C, float slope, float eps, void* stream) {
-  FDM_CHECK_ARG(x && out && B > 0 && T > 0 && C > 0 && t_stride >= T, "fdm_leaky_instnorm: bad arguments");
+                                  int64_t t_stride, int64_t out_t_stride, int64_t C, float slope, float eps, void* stream) {
+  FDM_CHECK_ARG(x && out && B > 0 && T > 0 && C > 0 && t_stride >= T && out_t_stride >= T, "fdm_leaky_instnorm: bad arguments");
+  FDM_CHECK_ARG(x != out || t_stride == out_t_stride, "fdm_leaky_instnorm: in-place needs equal strides");
   dim3 grid(static_cast<unsigned>(ceil_div64(C, 32)), static_cast<unsigned>(B));
   leaky_instnorm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, out, out_dtype, static_cast<int>(T),
-                                                                                  t_stride, static_cast<int>(C), slope, eps);
+                                                                                  t_stride, out_t_stride, static_cast<int>(C), slope, eps);
   FDM_CHECK_LAUNCH();
   return 0;
 }

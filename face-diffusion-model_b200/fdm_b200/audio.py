@@ -1,0 +1,149 @@
+"""Audio-encoder engine: HuBERT-large / wav2vec2 forward on libfdm_b200 kernels, run ONCE per clip batch.
+
+Replaces HubertModel.forward (reference models/hubert.py:75-146, which the reference re-runs inside every
+denoising step, models/fdm_vocaset.py:59) and the HF `transformers` modules it calls (feature encoder,
+feature projection, positional conv embedding, encoder layers). The HF module is kept only as the parameter
+container so checkpoints / state_dict keys stay identical.
+
+Layout: channel-last activations [clip, frame, channel] with a per-clip padded frame stride, so that
+  * each stride-2 conv of the feature encoder is ONE GEMM over overlapping rows (lda = 2*C_in, K = k*C_in),
+  * the grouped positional conv (k = 128, 16 groups) is 16 GEMMs whose TMA producer shifts the row coordinate
+    per filter tap (implicit im2col),
+  * LayerNorm+GELU, residual adds and biases ride in the GEMM / norm epilogues.
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+
+from . import lib
+
+
+class AudioEncoderEngine:
+    def __init__(self, hf_model: torch.nn.Module, precision: str = "bf16"):
+        assert precision in ("bf16", "fp32")
+        self.m = hf_model
+        self.cfg = hf_model.config
+        self.precision = precision
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self._packed_key = None
+        cfg = self.cfg
+        if cfg.feat_extract_norm != "layer" or not cfg.do_stable_layer_norm:
+            raise NotImplementedError("only the layer-norm feature encoder + stable-layer-norm encoder "
+                                      "(hubert-large-ls960-ft family) is implemented on the CUDA path")
+        assert cfg.conv_kernel[0] == 10 and cfg.conv_stride[0] == 5 and all(s == 2 for s in cfg.conv_stride[1:])
+        assert cfg.hidden_act == "gelu" and cfg.feat_extract_activation == "gelu"
+
+    def pack(self, force: bool = False) -> None:
+        sd = self.m.state_dict()
+        key = (self.precision,) + tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        if not force and key == self._packed_key:
+            return
+        cfg, m = self.cfg, self.m
+        dev = next(m.parameters()).device
+        assert dev.type == "cuda", "audio encoder must live on a CUDA device (no CPU fallback)"
+        W = lambda t: t.detach().to(self.dtype).contiguous()
+        Fv = lambda t: t.detach().float().contiguous()
+        w = {}
+        convs = m.feature_extractor.conv_layers
+        c0 = convs[0]
+        w["c0_w"] = Fv(c0.conv.weight.reshape(c0.conv.weight.shape[0], -1))
+        w["c0_b"], w["c0_g"], w["c0_beta"] = Fv(c0.conv.bias), Fv(c0.layer_norm.weight), Fv(c0.layer_norm.bias)
+        w["convs"] = []
+        for layer in convs[1:]:
+            cw = layer.conv.weight  # [Cout, Cin, k] -> [Cout, k, Cin] (tap-major K, matching overlapping rows)
+            w["convs"].append(dict(w=W(cw.permute(0, 2, 1).reshape(cw.shape[0], -1)), b=Fv(layer.conv.bias),
+                                   g=Fv(layer.layer_norm.weight), beta=Fv(layer.layer_norm.bias), k=cw.shape[2]))
+        fp = m.feature_projection
+        w["fp_g"], w["fp_beta"] = Fv(fp.layer_norm.weight), Fv(fp.layer_norm.bias)
+        w["fp_w"], w["fp_b"] = W(fp.projection.weight), Fv(fp.projection.bias)
+        pc = m.encoder.pos_conv_embed.conv
+        pw = pc.weight.detach()  # weight-norm parametrisation resolved by torch: [C, C/groups, k]
+        G = cfg.num_conv_pos_embedding_groups
+        C = cfg.hidden_size
+        cg = C // G
+        w["pos_w"] = [W(pw[g * cg:(g + 1) * cg].permute(0, 2, 1).reshape(cg, -1)) for g in range(G)]
+        w["pos_b"] = [Fv(pc.bias[g * cg:(g + 1) * cg]) for g in range(G)]
+        w["layers"] = []
+        for lyr in m.encoder.layers:
+            a = lyr.attention
+            w["layers"].append(dict(
+                ln1_g=Fv(lyr.layer_norm.weight), ln1_b=Fv(lyr.layer_norm.bias),
+                qkv_w=W(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
+                qkv_b=Fv(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
+                o_w=W(a.out_proj.weight), o_b=Fv(a.out_proj.bias),
+                ln2_g=Fv(lyr.final_layer_norm.weight), ln2_b=Fv(lyr.final_layer_norm.bias),
+                f1_w=W(lyr.feed_forward.intermediate_dense.weight), f1_b=Fv(lyr.feed_forward.intermediate_dense.bias),
+                f2_w=W(lyr.feed_forward.output_dense.weight), f2_b=Fv(lyr.feed_forward.output_dense.bias)))
+        w["ln_g"], w["ln_b"] = Fv(m.encoder.layer_norm.weight), Fv(m.encoder.layer_norm.bias)
+        self.w, self.dev, self._packed_key = w, dev, key
+
+    def frame_counts(self, n_samples: int) -> List[int]:
+        out, n = [], n_samples
+        for k, s in zip(self.cfg.conv_kernel, self.cfg.conv_stride):
+            n = (n - k) // s + 1
+            out.append(n)
+        return out
+
+    @torch.no_grad()
+    def encode(self, audio: torch.Tensor) -> torch.Tensor:
+        """audio (B, L) fp32 on device -> last_hidden_state (B, N, hidden) in the compute dtype, N even."""
+        self.pack()
+        cfg, w, dev, dt = self.cfg, self.w, self.dev, self.dtype
+        assert audio.dim() == 2 and audio.dtype == torch.float32 and audio.is_cuda
+        audio = audio.contiguous()
+        B, L = audio.shape
+        lens = self.frame_counts(L)
+        n_conv = len(lens)
+        # padded per-clip strides: exact doubling between consecutive stride-2 layers
+        last = max(math.ceil(lens[i] / 2 ** (n_conv - 1 - i)) for i in range(n_conv))
+        last = (last + 7) // 8 * 8
+        strides = [last * 2 ** (n_conv - 1 - i) for i in range(n_conv)]
+        Cc = cfg.conv_dim[0]
+        slack = 2
+        cur = torch.zeros(B * strides[0] + slack, Cc, device=dev, dtype=dt)
+        lib.hubert_conv0(audio, w["c0_w"], w["c0_b"], w["c0_g"], w["c0_beta"], cur, lens[0], strides[0], Cc)
+        for i, cv in enumerate(w["convs"], start=1):
+            nxt = torch.zeros(B * strides[i] + slack, cfg.conv_dim[i], device=dev, dtype=dt)
+            M = B * strides[i]
+            lib.gemm(cur, cv["w"], nxt, bias=cv["b"], M=M, lda=2 * cfg.conv_dim[i - 1], a_rows=M, K=cv["k"] * cfg.conv_dim[i - 1])
+            lib.layernorm(nxt[:M], nxt[:M], g1=cv["g"], b1=cv["beta"], act1=lib.ACT_GELU_ERF)
+            cur = nxt
+        N = lens[-1] - (lens[-1] % 2)  # models/hubert.py:95-96: drop an odd last frame
+        Lp = strides[-1]
+        C = cfg.hidden_size
+        M = B * Lp
+        lib.layernorm(cur[:M], cur[:M], g1=w["fp_g"], b1=w["fp_beta"], eps=cfg.layer_norm_eps)
+        hid = torch.empty(M, C, device=dev, dtype=dt)
+        lib.gemm(cur[:M], w["fp_w"], hid, bias=w["fp_b"])
+        # positional conv embedding: zero padding k/2 both sides, grouped conv as per-tap row-shifted GEMMs
+        kpos, G = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        cg = C // G
+        pad = kpos // 2
+        Tp = (N + 2 * pad + 7) // 8 * 8
+        xpad = torch.zeros(B * Tp, C, device=dev, dtype=dt)
+        lib.pad_time(hid, xpad, B, N, C, pad, Tp - N - pad, 0, src_t_stride=Lp)
+        x = torch.zeros(B * Tp, C, device=dev, dtype=dt)
+        Mp = B * Tp - (kpos - 1)
+        for g in range(G):
+            lib.gemm(xpad[:, g * cg:], w["pos_w"][g], x[:, g * cg:(g + 1) * cg], bias=w["pos_b"][g], act=lib.ACT_GELU_ERF,
+                     residual=xpad[pad:, g * cg:(g + 1) * cg], M=Mp, lda=C, a_rows=B * Tp, taps=kpos, tap_k=cg, tap_row_shift=1)
+        H = cfg.num_attention_heads
+        dh = C // H
+        qkv = torch.empty(B * Tp, 3 * C, device=dev, dtype=dt)
+        y = torch.empty(B * Tp, C, device=dev, dtype=dt)
+        att = torch.zeros(B * Tp, C, device=dev, dtype=dt)
+        ffn = torch.empty(B * Tp, cfg.intermediate_size, device=dev, dtype=dt)
+        eps = cfg.layer_norm_eps
+        for Lw in w["layers"]:
+            lib.layernorm(x, y, g1=Lw["ln1_g"], b1=Lw["ln1_b"], eps=eps)
+            lib.gemm(y, Lw["qkv_w"], qkv, bias=Lw["qkv_b"])
+            lib.self_attention(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, B, N, Tp, H, dh, dh ** -0.5)
+            lib.gemm(att, Lw["o_w"], x, bias=Lw["o_b"], residual=x)
+            lib.layernorm(x, y, g1=Lw["ln2_g"], b1=Lw["ln2_b"], eps=eps)
+            lib.gemm(y, Lw["f1_w"], ffn, bias=Lw["f1_b"], act=lib.ACT_GELU_ERF)
+            lib.gemm(ffn, Lw["f2_w"], x, bias=Lw["f2_b"], residual=x)
+        lib.layernorm(x, y, g1=w["ln_g"], b1=w["ln_b"], eps=eps)
+        return y.view(B, Tp, C)[:, :N]

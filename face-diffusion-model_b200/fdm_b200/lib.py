@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 class NormArgs(C.Structure):
     _fields_ = [("x", _vp), ("ldx", _i64), ("x_dtype", _i32), ("r1", _vp), ("ldr1", _i64), ("r1_dtype", _i32),
                 ("g1", _vp), ("b1", _vp), ("act1", _i32), ("r2", _vp), ("ldr2", _i64), ("r2_dtype", _i32),
-                ("vec2", _vp), ("vec_index_dev", _vp), ("g2", _vp), ("b2", _vp), ("out", _vp), ("ldo", _i64),
+                ("r2_rows", _i64), ("vec2", _vp), ("vec_index_dev", _vp), ("g2", _vp), ("b2", _vp), ("out", _vp), ("ldo", _i64),
                 ("out_dtype", _i32), ("out2", _vp), ("ldo2", _i64), ("out2_dtype", _i32), ("rows", _i64),
                 ("d", _i64), ("eps", _f32)]
 
@@ -45,7 +45,7 @@ class AttnArgs(C.Structure):
 class DdpmArgs(C.Structure):
     _fields_ = [("x0_cond", _vp), ("x0_uncond", _vp), ("guidance", _f32), ("x_t", _vp), ("noise", _vp),
                 ("out", _vp), ("out_bf16", _vp), ("c1", _vp), ("c2", _vp), ("sigma", _vp), ("t_per_clip", _vp),
-                ("t_sched", _vp), ("cursor_dev", _vp), ("B", _i64), ("elems_per_clip", _i64), ("seed", _u64),
+                ("t_dev", _vp), ("B", _i64), ("elems_per_clip", _i64), ("seed", _u64),
                 ("clip_index0", _i64)]
 
 
@@ -56,10 +56,10 @@ EXPORTS = {
     "fdm_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_layernorm": (C.c_int, [C.POINTER(NormArgs), _vp]),
-    "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
+    "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
     "fdm_self_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "fdm_ddpm_step": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
-    "fdm_advance_cursor": (C.c_int, [_vp, _vp]),
+    "fdm_advance_cursor": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "fdm_philox_normal": (C.c_int, [_vp, _i64, _i64, _u64, _i64, _i32, _vp]),
     "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
@@ -189,7 +189,10 @@ def layernorm(x: torch.Tensor, out: torch.Tensor, g1=None, b1=None, r1=None, act
     if r1 is not None:
         r = two_d(r1); n.r1, n.ldr1, n.r1_dtype = _ptr(r), r.stride(0), _dt(r)
     if r2 is not None:
-        r = two_d(r2); n.r2, n.ldr2, n.r2_dtype = _ptr(r), r.stride(0), _dt(r)
+        r = r2.reshape(-1, d) if r2.is_contiguous() else r2
+        assert r.dim() == 2 and r.stride(1) == 1 and x2.shape[0] % r.shape[0] == 0
+        n.r2, n.ldr2, n.r2_dtype = _ptr(r), r.stride(0), _dt(r)
+        n.r2_rows = 0 if r.shape[0] == x2.shape[0] else r.shape[0]
     n.g1, n.b1, n.g2, n.b2 = _ptr(g1), _ptr(b1), _ptr(g2), _ptr(b2)
     n.act1 = act1
     n.vec2, n.vec_index_dev = _ptr(vec2), _ptr(vec_index_dev)
@@ -203,9 +206,10 @@ def layernorm(x: torch.Tensor, out: torch.Tensor, g1=None, b1=None, r1=None, act
 
 
 def leaky_instnorm(x: torch.Tensor, out: torch.Tensor, B: int, T: int, t_stride: int, Cn: int,
-                   slope: float = 0.2, eps: float = 1e-5) -> torch.Tensor:
+                   slope: float = 0.2, eps: float = 1e-5, out_t_stride: Optional[int] = None) -> torch.Tensor:
     lib = require_device()
-    _check(lib.fdm_leaky_instnorm(_ptr(x), _dt(x), _ptr(out), _dt(out), B, T, t_stride, Cn, slope, eps, _stream()))
+    _check(lib.fdm_leaky_instnorm(_ptr(x), _dt(x), _ptr(out), _dt(out), B, T, t_stride,
+                                  out_t_stride if out_t_stride is not None else t_stride, Cn, slope, eps, _stream()))
     _launched()
     return out
 
@@ -229,7 +233,7 @@ def self_attention(q, k, v, out, B: int, T: int, t_stride: int, H: int, dh: int,
 
 
 def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: float = 0.0, noise=None,
-              out_bf16=None, t_per_clip=None, t_sched=None, cursor=None, seed: int = 0,
+              out_bf16=None, t_per_clip=None, t_dev=None, seed: int = 0,
               clip_index0: int = 0) -> torch.Tensor:
     lib = require_device()
     a = DdpmArgs()
@@ -241,7 +245,7 @@ def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: flo
     a.c1, a.c2, a.sigma = _ptr(c1), _ptr(c2), _ptr(sigma)
     if t_per_clip is not None:
         assert t_per_clip.dtype == torch.int64 and t_per_clip.numel() == B
-    a.t_per_clip, a.t_sched, a.cursor_dev = _ptr(t_per_clip), _ptr(t_sched), _ptr(cursor)
+    a.t_per_clip, a.t_dev = _ptr(t_per_clip), _ptr(t_dev)
     a.B, a.elems_per_clip = B, x_t.numel() // B
     a.seed, a.clip_index0 = seed, clip_index0
     _check(lib.fdm_ddpm_step(C.byref(a), _stream()))
@@ -249,8 +253,9 @@ def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: flo
     return out
 
 
-def advance_cursor(cursor: torch.Tensor) -> None:
-    _check(require_device().fdm_advance_cursor(_ptr(cursor), _stream()))
+def advance_cursor(cursor: torch.Tensor, t_sched: torch.Tensor, t_dev: torch.Tensor) -> None:
+    assert cursor.dtype == t_sched.dtype == t_dev.dtype == torch.int32
+    _check(require_device().fdm_advance_cursor(_ptr(cursor), _ptr(t_sched), t_sched.numel(), _ptr(t_dev), _stream()))
     _launched()
 
 

@@ -1,0 +1,110 @@
+"""Sampling-loop engine: the DDPM ancestral loop (and DDIM) as a CUDA-graph replay of one fused step.
+
+Replaces GaussianDiffusion.p_sample_loop / p_sample / p_mean_variance / q_posterior (reference
+video_diffusion_pytorch/diffusion_mead_encoder_decoder.py:632-671, diffusion_BIWI_encoder_decoder.py:632-710).
+One step = DenoiserEngine.denoise (all layers) + ONE fused update kernel (CFG combine + posterior mean + noise
+add, csrc/ddpm.cu) + a 1-thread kernel that advances the device-resident step counter; nothing in a step
+touches the host, so the whole step is captured once and replayed for every t.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence, Union
+
+import torch
+
+from . import lib
+from .denoiser import DenoiserEngine
+
+NoiseSpec = Union[None, str, Callable[[int], torch.Tensor]]
+
+
+class SamplerEngine:
+    def __init__(self, denoiser: DenoiserEngine, c1: torch.Tensor, c2: torch.Tensor, sigma: torch.Tensor,
+                 guidance_level: Optional[float] = None):
+        self.den = denoiser
+        self.c1, self.c2, self.sigma = c1, c2, sigma
+        self.level = guidance_level
+        self.last_step_ms = None
+
+    @torch.no_grad()
+    def run(self, x_T: torch.Tensor, steps: Sequence[int], noise: NoiseSpec = "philox", seed: int = 0,
+            clip_index0: int = 0, graph: bool = True, tap: Optional[Callable[[int, torch.Tensor], None]] = None,
+            time_steps: bool = False) -> torch.Tensor:
+        """x_T (B, fq*T, zdim) fp32 on device; steps: the t values in execution order (e.g. 999..0).
+        noise: "philox" (in-kernel counter-based generator), or a callable t -> tensor (host- or device-side,
+        same shape as x_T) that is copied in before every step with t > 0 (parity runs)."""
+        den = self.den
+        B, T, d, S = den.B, den.T, den.P.d, den.passes
+        assert x_T.is_cuda and x_T.dtype == torch.float32 and x_T.numel() == B * T * d, "x_T does not match prepare()"
+        assert (S == 2) == (self.level is not None), "guidance passes and guidance level disagree"
+        dev = x_T.device
+        steps = list(steps)
+        x = x_T.contiguous().clone()
+        xin_bf = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16) if den.dtype == torch.bfloat16 else None
+        xin = xin_bf if xin_bf is not None else x.view(B * T, d)
+        sched = torch.tensor(steps, dtype=torch.int32, device=dev)
+        cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+        t_dev = sched[:1].clone()
+        host_noise = callable(noise)
+        noise_buf = torch.empty_like(x) if host_noise else None
+        assert host_noise or noise in (None, "philox")
+
+        def step_body():
+            x0 = den.denoise(xin, t_dev)
+            lib.ddpm_step(x0[0], x, x, self.c1, self.c2, self.sigma, x0_uncond=x0[1] if S == 2 else None,
+                          guidance=float(self.level) if S == 2 else 0.0, noise=noise_buf, out_bf16=xin_bf, t_dev=t_dev,
+                          seed=seed, clip_index0=clip_index0)
+            lib.advance_cursor(cursor, sched, t_dev)
+
+        def reset():
+            x.copy_(x_T.reshape(x.shape))
+            if xin_bf is not None:
+                lib.cast(x, xin_bf.view(x.shape))
+            cursor.zero_()
+            t_dev.copy_(sched[:1])
+
+        def feed_noise(t):
+            if host_noise and t > 0:
+                n = noise(t)
+                noise_buf.copy_(n.reshape(noise_buf.shape), non_blocking=True)
+
+        use_graph = graph and tap is None
+        if use_graph:
+            reset()
+            if host_noise:
+                noise_buf.zero_()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_body()  # warm-up outside capture (function attributes, lazy module loading)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            reset()
+            n_before = lib.launch_count
+            with torch.cuda.graph(g):
+                step_body()
+            per_step = lib.launch_count - n_before
+            reset()
+            evs = None
+            if time_steps:
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(steps) + 1)]
+                evs[0].record()
+            for i, t in enumerate(steps):
+                feed_noise(t)
+                g.replay()
+                lib._launched(per_step)
+                if evs is not None:
+                    evs[i + 1].record()
+            if evs is not None:
+                torch.cuda.synchronize()
+                ms = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(len(steps)))
+                self.last_step_ms = ms[len(ms) // 2]
+        else:
+            reset()
+            for t in steps:
+                feed_noise(t)
+                if tap is not None:
+                    x0 = den.denoise(xin, t_dev)
+                    tap(t, x0.clone())
+                step_body()  # (recomputes the denoiser when tapping: taps are a debugging aid)
+        return x.view(x_T.shape)

@@ -78,7 +78,9 @@ int fdm_gemm_f32(const fdm_gemm_args* args, void* stream);
  * Row LayerNorm with fused residual adds; replaces norm1/2/3 of nn.TransformerDecoderLayer
  * (post-norm, eps 1e-5), base_models.Norm (models/lib/base_models.py:37-52) and HF HuBERT LNs.
  *   y = x + r1 (if r1)            ; y = LN(y; g1, b1)  (if g1)  ; y = act1(y)
- *   if g2: y = y + r2 (if r2) + vec2[vec_index * d .. ] (if vec2) ; y = LN(y; g2, b2)
+ *   if g2: y = y + r2[row % r2_rows] (if r2) + vec2[vec_index * d .. ] (if vec2) ; y = LN(y; g2, b2)
+ *          (r2_rows = 0 means r2 has one row per input row; otherwise r2 is shared by row blocks, e.g. by the
+ *           conditional and unconditional guidance passes)
  * out (out_dtype) and optional out2 (the other dtype) receive y.
  * vec_index is read on the device from *vec_index_dev (the denoising step t) when vec2 != NULL.
  */
@@ -87,7 +89,7 @@ typedef struct fdm_norm_args {
   const void* r1; int64_t ldr1; int32_t r1_dtype;
   const float* g1; const float* b1;
   int32_t act1;
-  const void* r2; int64_t ldr2; int32_t r2_dtype;
+  const void* r2; int64_t ldr2; int32_t r2_dtype; int64_t r2_rows;
   const float* vec2; const int32_t* vec_index_dev;
   const float* g2; const float* b2;
   void* out; int64_t ldo; int32_t out_dtype;
@@ -98,10 +100,11 @@ typedef struct fdm_norm_args {
 int fdm_layernorm(const fdm_norm_args* args, void* stream);
 
 /* LeakyReLU(0.2) + InstanceNorm1d over time (affine=False, eps, biased variance) on a
- * [B, T(ld rows per clip = t_stride), C] activation; models/vq_vae_vocaset.py:194-199. */
+ * [B, T (t_stride rows per clip), C] activation, written with out_t_stride rows per clip (this also
+ * compacts the padded conv output); models/vq_vae_vocaset.py:194-199. */
 int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int32_t out_dtype,
-                       int64_t B, int64_t T, int64_t t_stride, int64_t C, float slope, float eps,
-                       void* stream);
+                       int64_t B, int64_t T, int64_t t_stride, int64_t out_t_stride, int64_t C,
+                       float slope, float eps, void* stream);
 
 /* ---- attention ---------------------------------------------------------------- *
  * O[b,t,h,:] = softmax_j( scale * Q[b,t,h,:].K[b,j,h,:] + bias(h,t,j) ) V[b,j,h,:]
@@ -126,8 +129,8 @@ int fdm_self_attention(const fdm_attn_args* args, void* stream);
  *   x0   = x0_uncond + guidance * (x0_cond - x0_uncond)      (utiles/classifierfree.py:20-21; skipped if x0_uncond == NULL)
  *   mean = c1[t]*x0 + c2[t]*x_t                              (diffusion_BIWI_encoder_decoder.py:632-639)
  *   out  = mean + sigma[t]*noise   (no noise when t == 0)    (diffusion_BIWI_encoder_decoder.py:650-656)
- * t comes from t_per_clip[b] (int64, p_sample API) or, if NULL, from t_sched[*cursor_dev]
- * (CUDA-graph replay without host sync). noise == NULL selects the in-kernel Philox4x32-10 +
+ * t comes from t_per_clip[b] (int64, p_sample API) or, if NULL, from *t_dev (device-resident step
+ * counter: CUDA-graph replay without host sync). noise == NULL selects the in-kernel Philox4x32-10 +
  * Box-Muller generator keyed by (seed, clip_index0 + b, t, element). Products and sums are
  * individually rounded (no FMA contraction) to match the PyTorch expression bit for bit.
  * out_bf16 (optional) receives a bf16 copy of out for the next step's first GEMM.
@@ -137,13 +140,13 @@ typedef struct fdm_ddpm_args {
   const float* x_t; const float* noise;
   float* out; void* out_bf16;
   const float* c1; const float* c2; const float* sigma;    /* [num_timesteps] tables */
-  const int64_t* t_per_clip; const int32_t* t_sched; const int32_t* cursor_dev;
+  const int64_t* t_per_clip; const int32_t* t_dev;
   int64_t B; int64_t elems_per_clip;
   uint64_t seed; int64_t clip_index0;
 } fdm_ddpm_args;
 int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream);
-/* cursor_dev[0] += 1 (end of a graph-replayed step). */
-int fdm_advance_cursor(int32_t* cursor_dev, void* stream);
+/* End of a graph-replayed step: cursor[0] += 1; t_dev[0] = t_sched[min(cursor[0], n_sched-1)]. */
+int fdm_advance_cursor(int32_t* cursor_dev, const int32_t* t_sched, int32_t n_sched, int32_t* t_dev, void* stream);
 /* Fill out[B*elems_per_clip] with the same Philox normals the fused step would draw for step t. */
 int fdm_philox_normal(float* out, int64_t B, int64_t elems_per_clip, uint64_t seed,
                       int64_t clip_index0, int32_t t, void* stream);

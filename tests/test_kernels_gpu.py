@@ -191,13 +191,14 @@ def test_ddpm_step_bit_exact(cuda_dev):
     ref = e(tabs[0]) * x0 + e(tabs[1]) * xt + e(tabs[2]) * nz * (t > 0)[:, None]
     assert torch.equal(out, ref)
     assert torch.equal(ob, ref.bfloat16())
-    # graph-style addressing: t from t_sched[*cursor]
+    # graph-style addressing: t from a device-resident step counter
     sched = torch.arange(999, -1, -1, dtype=torch.int32, device=cuda_dev)
     cur = torch.tensor([499], dtype=torch.int32, device=cuda_dev)
-    lib.ddpm_step(c, xt, out, *tabs, noise=nz, t_sched=sched, cursor=cur)
-    lib.advance_cursor(cur)
+    t_dev = sched[499:500].clone()
+    lib.ddpm_step(c, xt, out, *tabs, noise=nz, t_dev=t_dev)
+    lib.advance_cursor(cur, sched, t_dev)
     torch.cuda.synchronize()
-    assert cur.item() == 500
+    assert cur.item() == 500 and t_dev.item() == 499
     assert torch.equal(out, tabs[0][500] * c + tabs[1][500] * xt + tabs[2][500] * nz)
 
 
