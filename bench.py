@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py — LG-LDM sampling throughput on B200 (BASELINE.json metric: animated frames/s over the full DDPM loop).
+
+A "step" is one complete sampling job over one batch of synthetic clips: audio encoder (once) -> 1000-step DDPM
+loop with classifier-free guidance (CUDA-graph replay of the fused step) -> EVQ-VAE quantise -> decode to
+vertices (-> NCCL all-gather of the vertex sequences when N > 1). Workload at N = 1: BASELINE.json configs[1],
+"VOCASET LG-LDM sampling, batch 64 clips x 4 s with classifier-free guidance on 1 B200"; for N > 1 every rank
+runs that workload on its own shard of clips (weak scaling) and the vertices are all-gathered.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "face-diffusion-model_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "animated frames/sec (full DDPM loop)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU")
+    ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--ddpm-steps", type=int, default=1000)
+    ap.add_argument("--preset", default="vocaset", choices=["vocaset", "mead"])
+    ap.add_argument("--no-cfg", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-steps", type=int, default=4, help="DDPM steps per bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def build_models(preset, device, precision):
+    import warnings
+    warnings.simplefilter("ignore")
+    torch.manual_seed(0)
+    if preset == "vocaset":
+        from models.fdm_vocaset import FDM
+        from models.vq_vae_vocaset import VQAutoEncoder
+        from models.utils.config import vocaset_vq_vae_args as vargs
+        from video_diffusion_pytorch.diffusion_BIWI_encoder_decoder import GaussianDiffusion
+        fdm = FDM(feature_dim=1024)
+    else:
+        from models.fdm_vqvae_mead import FDM
+        from models.vq_vae_emotion import VQAutoEncoder
+        from utiles.args import vq_vae_args as vargs
+        from video_diffusion_pytorch.diffusion_mead_encoder_decoder import GaussianDiffusion
+        fdm = FDM(feature_dim=512, vertice_dim=5023 * 3, struct="Dec")
+    torch.nn.init.normal_(fdm.latent_decoder.weight, std=0.02)  # reference zero-init would make x0_hat == 0
+    ae = VQAutoEncoder(vargs())
+    torch.nn.init.normal_(ae.quantize.embedding.weight)
+    diff = GaussianDiffusion(fdm, timesteps=1000, loss_type="l2")
+    if device is not None:
+        fdm.set_precision(precision)
+        ae.set_precision(precision)
+        diff.to(device)
+        ae.to(device)
+    return fdm.eval(), ae.eval(), diff.eval()
+
+
+def synthetic_audio(n_clips, n_samples, clip0):
+    out = torch.empty(n_clips, n_samples)
+    for i in range(n_clips):
+        g = torch.Generator(device="cpu").manual_seed(1234 + clip0 + i)
+        a = torch.randn(n_samples, generator=g)
+        out[i] = (a - a.mean()) / a.std()
+    return out
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, pw) if p > 0.5 * max(pw)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+# --------------------------------------------------------------------------------------------------
+# per-kernel timing of one eager denoiser step (roofline evidence)
+# --------------------------------------------------------------------------------------------------
+def profile_step(eng, sampler_args, repeats=3):
+    """Times every library launch of one denoiser evaluation + fused update with CUDA events on the launching
+    stream (eager, not under the graph) and aggregates by kernel class."""
+    from fdm_b200 import lib
+    records = []
+    orig = {n: getattr(lib, n) for n in ("gemm", "layernorm", "self_attention", "ddpm_step")}
+
+    def wrap(name):
+        fn = orig[name]
+
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            work = 0.0
+            if name == "gemm":
+                aa, w = a[0], a[1]
+                M = k.get("M") or aa.shape[0]
+                work = 2.0 * M * w.shape[0] * w.shape[1]
+                cls = "gemm_bf16_tcgen05" if aa.dtype == torch.bfloat16 else "gemm_f32"
+            elif name == "ddpm_step":
+                cls = "ddpm_step"
+            else:
+                cls = name
+            records.append((cls, work, e0, e1))
+            return r
+        return inner
+
+    x_in, t_dev, ddpm = sampler_args
+    try:
+        for n in orig:
+            setattr(lib, n, wrap(n))
+        for _ in range(repeats):
+            x0 = eng.denoise(x_in, t_dev)
+            ddpm(x0)
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in orig.items():
+            setattr(lib, n, fn)
+    agg = {}
+    for cls, work, e0, e1 in records:
+        a = agg.setdefault(cls, dict(ms=0.0, work=0.0, launches=0))
+        a["ms"] += e0.elapsed_time(e1)
+        a["work"] += work
+        a["launches"] += 1
+    for a in agg.values():
+        a["ms"] /= repeats
+        a["work"] /= repeats
+        a["launches"] //= repeats
+    return agg
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_sample(args, n_ddpm_steps):
+    """Runs the reference's algorithm as the reference runs it (B = 1, audio encoder re-evaluated inside every
+    denoiser call, two denoiser calls per step with guidance) for `n_ddpm_steps` steps of one clip, plus one
+    quantise + decode, and extrapolates to the full `ddpm_steps` chain. Returns (frames/s, detail)."""
+    from oracle import reference_ops as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    fdm, ae, diff = build_models(args.preset, None, "fp32")
+    P = R.PRESETS[args.preset]
+    sd = {k: v.detach() for k, v in fdm.state_dict().items()}
+    from transformers import HubertModel
+    hf = HubertModel(R.audio_encoder_config("hubert", False)).eval()
+    hf.load_state_dict({k[len("audio_encoder."):]: v for k, v in sd.items() if k.startswith("audio_encoder.")})
+    n_samples = int(16000 * args.seconds)
+    audio = synthetic_audio(1, n_samples, 0)[0]
+    idh = torch.eye(P["n_id"])[0][None]
+    emo = torch.eye(7)[4][None] if P["emotion"] else None
+    tabs = R.diffusion_tables(1000)
+    with torch.no_grad():
+        hidden = R.audio_encode(hf, audio)
+        T = hidden.shape[0] // (2 if P["pair"] else 1)
+        x = torch.randn(T * P["fq"], P["zdim"])
+
+        def denoise_as_is(z, t, idh_, emo_):
+            h = R.audio_encode(hf, audio)  # the reference re-runs the audio encoder in every forward
+            return R.fdm_forward(sd, args.preset, h, t, z, idh_, emo_)
+
+        def step(z, t):
+            if args.no_cfg:
+                x0 = denoise_as_is(z, t, idh, emo)
+            elif P["emotion"]:
+                x0 = R.cfg_forward(lambda oh: denoise_as_is(z, t, idh, oh), emo, 2.5)
+            else:
+                x0 = R.cfg_forward(lambda oh: denoise_as_is(z, t, oh, None), idh, 2.5)
+            return R.p_sample(tabs, x0, z, t, torch.randn_like(z))
+
+        step(x, 999)  # warm-up
+        t0 = time.perf_counter()
+        for i in range(n_ddpm_steps):
+            x = step(x, 998 - i)
+        per_step = (time.perf_counter() - t0) / n_ddpm_steps
+        t0 = time.perf_counter()
+        idx, zq, _ = R.vq_quantize(x, ae.quantize.embedding.weight.detach(), 4 if P["emotion"] else None)
+        R.vq_decode({k: v.detach() for k, v in ae.state_dict().items()}, args.preset, zq)
+        tail = time.perf_counter() - t0
+    total = per_step * args.ddpm_steps + tail
+    return T / total, dict(s_per_ddpm_step=per_step, quant_decode_s=tail, frames=T, cores=torch.get_num_threads())
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cfg = not args.no_cfg
+    workload = (f"{args.preset.upper()} LG-LDM sampling, batch {args.clips} clips x {args.seconds:g} s "
+                f"{'with' if use_cfg else 'without'} classifier-free guidance, {args.ddpm_steps} DDPM steps, per GPU")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        sample = (f"1 clip x {args.seconds:g} s, {args.ref_sample_steps} DDPM steps as the reference runs them (audio encoder "
+                  f"re-run in every denoiser call, {'2 calls/step' if use_cfg else '1 call/step'}) + quantise + decode, "
+                  f"extrapolated to {args.ddpm_steps} steps")
+        detail = None
+        for i in range(args.warmup + args.steps):
+            fps, detail = cpu_reference_sample(args, args.ref_sample_steps)
+            if i >= args.warmup:
+                vals.append(fps)
+        v = sum(vals) / len(vals)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * detail["frames"] / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "impl": "oracle port of the reference PyTorch path on host cores"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": detail["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    from fdm_b200 import lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib.require_device()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from utiles.classifierfree import ClassifierFreeSampleModel
+    fdm, ae, diff = build_models(args.preset, dev, args.precision)
+    P = fdm.preset
+    if use_cfg:
+        diff.denoise_fn = ClassifierFreeSampleModel(fdm, level=2.5)
+    B = args.clips
+    n_samples = int(16000 * args.seconds)
+    clip0 = rank * B
+    audio_host = synthetic_audio(B, n_samples, clip0).pin_memory()
+    ids_host = torch.eye(P.n_id)[[(clip0 + i) % P.n_id for i in range(B)]].pin_memory()
+    emo_host = torch.eye(7)[[(clip0 + i) % 7 for i in range(B)]].pin_memory() if P.emotion else None
+    from fdm_b200.presets import conv_out_len
+    N = conv_out_len(n_samples)
+    N -= N % 2
+    T = N // 2 if P.pair_audio else N
+    shape = (B, T * P.fq, P.zdim)
+    diff.seed, diff.clip_index0, diff.noise_source = 20261017, clip0, "philox"
+    diff.time_steps = True
+    step_range = (1000, 1000 - args.ddpm_steps)
+    V3 = ae.args.in_dim
+    gathered = torch.empty(world * B, T, V3, device=dev) if world > 1 else None
+    verts_host = torch.empty(B, T, V3).pin_memory()
+
+    def job(audio_dev, ids_dev, emo_dev):
+        conds = (emo_dev, ids_dev) if P.emotion else (ids_dev,)
+        lat = diff.sample(audio_dev, shape, *conds, step_range=step_range)
+        zq, _, _ = ae.quant(lat, emo_dev) if P.emotion else ae.quant(lat)
+        verts = ae.decode(zq)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(gathered.view(-1), verts.view(-1))
+        return verts
+
+    def fresh_inputs():
+        # new device tensors per job so nothing is served from the per-clip caches of a previous job
+        a = audio_host.to(dev, non_blocking=True)
+        i = ids_host.to(dev, non_blocking=True)
+        e = emo_host.to(dev, non_blocking=True) if emo_host is not None else None
+        return a, i, e
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        job(*fresh_inputs())
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ---------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    inputs = [fresh_inputs() for _ in range(args.steps)]
+    barrier()
+    launches0 = lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    den_ms = []
+    for k in range(args.steps):
+        job(*inputs[k])
+        den_ms.append(diff.last_step_ms)
+    e1.record()
+    barrier()
+    launches = lib.launch_count - launches0
+    ms_dev = e0.elapsed_time(e1)
+    # ---- timed region 2: end to end through the public API with host buffers -------------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(args.steps):
+        v = job(*fresh_inputs())
+        verts_host.copy_(v, non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = t.tolist()
+    frames = world * B * T * args.steps
+    value = frames / (ms_dev / 1e3)
+    e2e = frames / (ms_e2e / 1e3)
+
+    # ---- roofline evidence: per-kernel event timing of one eager step ---------------------------------------
+    roof = None
+    extra = {}
+    if rank == 0:
+        pk = peaks()
+        eng = fdm.engine()
+        a_dev, i_dev, e_dev = fresh_inputs()
+        fdm.prepare(a_dev, T, i_dev, e_dev, guidance=(diff.denoise_fn.guidance_cond if use_cfg else None))
+        dt = eng.dtype
+        x = torch.randn(B, T * P.d, device=dev)
+        xin = x.view(B * T, P.d).to(dt)
+        xbf = torch.empty(B * T, P.d, device=dev, dtype=torch.bfloat16)
+        t_dev = torch.tensor([500], dtype=torch.int32, device=dev)
+
+        def ddpm(x0):
+            lib.ddpm_step(x0[0], x, x, diff.posterior_mean_coef1, diff.posterior_mean_coef2, diff._sigma_table(),
+                          x0_uncond=x0[1] if use_cfg else None, guidance=2.5, noise=None, out_bf16=xbf, t_dev=t_dev,
+                          seed=1, clip_index0=0)
+        agg = profile_step(eng, (xin, t_dev, ddpm))
+        tot_ms = sum(a["ms"] for a in agg.values())
+        shares = {k: round(a["ms"] / tot_ms, 4) for k, a in agg.items()}
+        g = agg.get("gemm_bf16_tcgen05") or agg.get("gemm_f32")
+        tf = g["work"] / (g["ms"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (fdm_gemm_bf16)" if "gemm_bf16_tcgen05" in agg else "gemm_f32_kernel",
+                "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+                "peak_source": f"{pk['src']} sustained bf16 cuBLAS (kernel timed inside the step)", "traffic": None,
+                "launches_per_denoise_step": g["launches"], "ms_per_denoise_step_in_kernel": g["ms"]}
+        d = agg["ddpm_step"]
+        elems = B * T * P.d
+        bytes_alg = elems * ((4 * 4 if use_cfg else 3 * 4) + 2)  # x0c,(x0u),x_t reads + fp32 write + bf16 copy; noise in-kernel
+        extra["ddpm_step_kernel"] = {"bound": "hbm", "achieved": bytes_alg / (d["ms"] / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                     "frac": bytes_alg / (d["ms"] / 1e3) / 1e9 / pk["hbm"], "bytes_per_launch": bytes_alg}
+        extra["kernel_time_shares_eager_step"] = shares
+        extra["eager_step_ms"] = tot_ms
+        extra["denoiser_tflops_in_loop"] = eng.flops_per_step() / (sorted(den_ms)[len(den_ms) // 2] / 1e3) / 1e12 if den_ms[0] else None
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        fps, detail = cpu_reference_sample(args, args.ref_sample_steps)
+        cpu_base = {"value": fps, "unit": UNIT, "cores": detail["cores"], "kind": "port",
+                    "sample": (f"oracle port, 1 clip x {args.seconds:g} s, {args.ref_sample_steps} DDPM steps as the reference runs them "
+                               f"(audio encoder re-run per denoiser call, guidance = 2 calls/step) + quantise + decode, extrapolated to "
+                               f"{args.ddpm_steps} steps; {detail['s_per_ddpm_step']:.3f} s/step")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": workload, "global_clips": world * B, "frames_per_clip": T, "ddpm_steps": args.ddpm_steps,
+                       "guidance": 2.5 if use_cfg else None, "noise": "in-kernel Philox4x32-10 keyed by global clip index",
+                       "parallelism": f"dp{world} (clips sharded, one all-gather of vertices)",
+                       "l2": "per-step working set (activations 2x52 MB + weights) exceeds nothing by design; every job uses fresh inputs, "
+                             "the 764 MB vertex write and 1000 graph replays flush L2 between jobs"},
+            "ms_per_denoise_step": sorted(den_ms)[len(den_ms) // 2] if den_ms and den_ms[0] else None,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(audio_host.numel() * 4 + ids_host.numel() * 4 +
+                                                                          (emo_host.numel() * 4 if emo_host is not None else 0)),
+                    "d2h_bytes_per_step": int(verts_host.numel() * 4)},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,7 @@ class DenoiserEngine:
         self.precision = precision
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self._packed_key = None
+        self.pack_serial = 0
         self.w = {}
         self.B = 0
         self.T = 0
@@ -100,6 +101,7 @@ class DenoiserEngine:
         self.w = w
         self.dev = dev
         self._packed_key = key
+        self.pack_serial += 1
 
     # ---- per-clip-batch state ---------------------------------------------------------------------
     def prepare(self, audio_hidden: torch.Tensor, n_frames: int, id_one_hot: torch.Tensor,

@@ -141,34 +141,50 @@ class FDMBase(nn.Module):
             self.__dict__["_prep_key"] = None
         return eng
 
+    @staticmethod
+    def _same(cached, tensors) -> bool:
+        """Cache hit only for the SAME tensor objects at the same version (a recycled allocation is a miss)."""
+        if cached is None or len(cached) != len(tensors):
+            return False
+        for (obj, ver), t in zip(cached, tensors):
+            if t is None:
+                if obj is not None:
+                    return False
+            elif obj is not t or ver != t._version:
+                return False
+        return True
+
+    @staticmethod
+    def _ident(tensors):
+        return tuple((t, None if t is None else t._version) for t in tensors)
+
     def encode_audio(self, audio: torch.Tensor) -> torch.Tensor:
-        """Audio-encoder output for a clip batch, cached on the identity of `audio` so that the reference's
-        per-step re-encoding (models/fdm_vocaset.py:59) costs one run per clip batch."""
-        key = (audio.data_ptr(), audio._version, tuple(audio.shape), self.precision)
+        """Audio-encoder output for a clip batch, cached on the identity (+ version counter) of the `audio` tensor so
+        that the reference's per-step re-encoding (models/fdm_vocaset.py:59) costs one run per clip batch."""
         c = self.__dict__["_audio_cache"]
-        if c is None or c[0] != key:
+        if c is None or not self._same(c[0], (audio,)) or c[1] != self.precision:
             if hasattr(self.audio_encoder, "precision"):
                 self.audio_encoder.precision = self.precision
             hidden = self.audio_encoder(audio).last_hidden_state
             want = torch.bfloat16 if self.precision == "bf16" else torch.float32
             assert hidden.dtype == want
-            c = (key, hidden.contiguous())
+            c = (self._ident((audio,)), self.precision, hidden.contiguous())
             self.__dict__["_audio_cache"] = c
-        return c[1]
+        return c[2]
 
     def set_audio_features(self, audio: torch.Tensor, hidden: torch.Tensor) -> None:
         """Register precomputed audio-encoder features (B, N, audio_dim) for `audio` (skips the encoder run)."""
         want = torch.bfloat16 if self.precision == "bf16" else torch.float32
-        key = (audio.data_ptr(), audio._version, tuple(audio.shape), self.precision)
-        self.__dict__["_audio_cache"] = (key, hidden.to(audio.device, want).contiguous())
+        self.__dict__["_audio_cache"] = (self._ident((audio,)), self.precision, hidden.to(audio.device, want).contiguous())
 
     def prepare(self, audio, n_frames: int, id_one_hot, emo_one_hot=None, guidance: Optional[str] = None) -> DenoiserEngine:
         eng = self.engine()
-        key = (audio.data_ptr(), audio._version, tuple(audio.shape), n_frames, id_one_hot.data_ptr(), id_one_hot._version,
-               None if emo_one_hot is None else (emo_one_hot.data_ptr(), emo_one_hot._version), guidance, eng._packed_key is None)
-        if self.__dict__["_prep_key"] != key or eng.B == 0:
+        eng.pack()
+        k = self.__dict__["_prep_key"]
+        meta = (n_frames, guidance, eng.pack_serial)
+        if k is None or k[1] != meta or not self._same(k[0], (audio, id_one_hot, emo_one_hot)) or eng.B == 0:
             eng.prepare(self.encode_audio(audio), n_frames, id_one_hot, emo_one_hot, guidance)
-            self.__dict__["_prep_key"] = (key[:-1] + (False,))
+            self.__dict__["_prep_key"] = (self._ident((audio, id_one_hot, emo_one_hot)), meta)
         return eng
 
     @torch.no_grad()
