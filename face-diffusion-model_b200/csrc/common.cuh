@@ -44,9 +44,11 @@ __device__ __forceinline__ void st_from_float(void* p, int32_t dtype, int64_t i,
 
 // ---- activations (match the PyTorch definitions used by the reference) -------------------------
 __device__ __forceinline__ float act_mish(float x) {
-  // x * tanh(softplus(x)), softplus threshold 20 as in ATen
-  float sp = x > 20.f ? x : log1pf(expf(x));
-  return x * tanhf(sp);
+  // x * tanh(softplus(x)) with tanh(log(1+e^x)) = n / (n + 2), n = e^x (e^x + 2); softplus threshold 20 as in ATen
+  if (x > 20.f) return x;
+  const float e = expf(x);
+  const float n = e * (e + 2.f);
+  return x * (n / (n + 2.f));
 }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float act_gelu_tanh(float x) {

@@ -30,8 +30,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int BAR_BYTES = 1024;                  // barriers + TMEM slot, keeps the staging tiles 1024-aligned
+  static constexpr int STAGING_BYTES = 4 * 2 * 4096;      // 4 epilogue warps x 2 tiles x (32 rows x 128 B)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024: manual alignment
 };
 
 struct Epilogue {
@@ -40,7 +41,8 @@ struct Epilogue {
   void* C;
   int64_t ldr, ldc;
   int32_t res_dtype, out_dtype, act;
-  int32_t vec_c, vec_r, vec_bias;  // 16-byte vector access is legal for full 32-column chunks
+  int32_t tma_c, vec_r, vec_bias;  // C through TMA stores; 16-byte vector access legal for residual / bias
+  int32_t M;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -144,20 +146,43 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- epilogue: one thread owns one output row, 32 consecutive columns per chunk -------------------
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const Epilogue& ep, int64_t row, int col0, int N) {
-  float v[32];
+// ---- epilogue ----------------------------------------------------------------------------------------
+// One thread owns one accumulator row (TMEM lane). A chunk is 128 bytes of output per row (64 bf16 or 32 fp32
+// columns): bias / activation / residual are applied in registers, the chunk is written row-wise into a per-warp
+// 32-row x 128-byte staging tile in the TMA 128B-swizzle layout (conflict-free 16-byte shared stores), and one
+// elected lane hands the tile to the TMA store engine (cp.async.bulk.tensor, clipped at the M/N edges). Two staging
+// tiles per warp let the store of chunk c overlap the math of chunk c+1. Row-per-thread global stores would cost
+// 32 LSU wavefronts per instruction; this path costs none.
+__device__ __forceinline__ void act_inplace(float (&v)[32], int act) {
+  if (act == FDM_ACT_NONE) return;
+  if (act == FDM_ACT_RELU) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == FDM_ACT_MISH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_mish(v[j]);
+  } else if (act == FDM_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_gelu_erf(v[j]);
+  } else if (act == FDM_ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_gelu_tanh(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  }
+}
+
+// bias + activation + residual for 32 consecutive columns [col0, col0+32) of output row `row`
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int64_t row, bool row_ok, int col0, int N) {
   const int ncols = min(32, N - col0);
   const bool full = ncols == 32;
-
   if (ep.bias) {
     if (full && ep.vec_bias) {
       const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
+        const float4 b = __ldg(b4 + j);
         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     } else {
@@ -166,22 +191,19 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
         if (j < ncols) v[j] += __ldg(ep.bias + col0 + j);
     }
   }
-  if (ep.act != FDM_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-  }
-  if (ep.residual) {
+  act_inplace(v, ep.act);
+  if (ep.residual && row_ok) {
     if (ep.res_dtype == FDM_BF16) {
       const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + row * ep.ldr + col0;
       if (full && ep.vec_r) {
         const uint4* r4 = reinterpret_cast<const uint4*>(r);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 u = __ldg(r4 + j);
+          const uint4 u = __ldg(r4 + j);
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float2 f = __bfloat1622float2(h[q]);
+            const float2 f = __bfloat1622float2(h[q]);
             v[8 * j + 2 * q] += f.x; v[8 * j + 2 * q + 1] += f.y;
           }
         }
@@ -196,7 +218,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
         const float4* r4 = reinterpret_cast<const float4*>(r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 b = __ldg(r4 + j);
+          const float4 b = __ldg(r4 + j);
           v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
         }
       } else {
@@ -206,42 +228,33 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
       }
     }
   }
-  if (ep.out_dtype == FDM_BF16) {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(ep.C) + row * ep.ldc + col0;
-    if (full && ep.vec_c) {
-      uint4* c4 = reinterpret_cast<uint4*>(c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 u;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
-        c4[j] = u;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) c[j] = __float2bfloat16_rn(v[j]);
-    }
-  } else {
-    float* c = reinterpret_cast<float*>(ep.C) + row * ep.ldc + col0;
-    if (full && ep.vec_c) {
-      float4* c4 = reinterpret_cast<float4*>(c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) c4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) c[j] = v[j];
-    }
-  }
 }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// staging tile: 32 rows x 128 bytes, 16-byte chunk index XOR (row & 7) == CU_TENSOR_MAP_SWIZZLE_128B
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) { return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
+               const __grid_constant__ CUtensorMap tmap_c, const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
                const int tap_row_shift, const int m_tiles, const int n_tiles) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -263,6 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (ep.tma_c) tma_prefetch_desc(&tmap_c);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -329,28 +343,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue warps: TMEM -> registers -> global =====
+    // ===== epilogue warps: TMEM -> registers -> swizzled smem staging -> TMA store =====
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
-    int acc = 0;
+    const uint32_t stage_base = bar_base + C::BAR_BYTES + static_cast<uint32_t>(warp - 2) * 8192u;
+    const bool out_bf16 = ep.out_dtype == FDM_BF16;
+    const int CW = out_bf16 ? 64 : 32;  // output columns per 128-byte staging row
+    int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const int64_t row = static_cast<int64_t>(m_blk) * BLOCK_M + quad * 32 + lane;
+      const int row_w = m_blk * BLOCK_M + quad * 32;  // first row of this warp's slab
+      const int64_t row = static_cast<int64_t>(row_w) + lane;
+      const bool row_ok = row < M;
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
+        const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        tmem_ld_wait();
-        if (row < M) epilogue_chunk(r, ep, row, col0, N);
+        const uint32_t sbuf = stage_base + buf * 4096u;
+        if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this tile
+        __syncwarp();
+        {
+          uint32_t r[32];
+          float v[32];
+          tmem_ld_32x32b_x32(tacc + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_math(v, ep, row, row_ok, col0, N);
+          if (out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(sbuf + stage_off(lane, j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                           pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(sbuf + stage_off(lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          }
+        }
+        if (out_bf16 && col0 + 32 < N) {  // second half of the 64-column bf16 chunk
+          uint32_t r[32];
+          float v[32];
+          tmem_ld_32x32b_x32(tacc + c0 + 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_math(v, ep, row, row_ok, col0 + 32, N);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(sbuf + stage_off(lane, 4 + j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                         pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+        }
+        if (ep.tma_c) {
+          fence_async_smem();  // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, sbuf, col0, row_w);  // rows >= M and columns >= N are clipped by the tensor map
+            bulk_commit();
+          }
+        } else {
+          // C rows are not 16-byte aligned (e.g. N = 15069 fp32): coalesced element stores, one row per iteration
+          __syncwarp();
+          const int esz = out_bf16 ? 2 : 4;
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t orow = static_cast<int64_t>(row_w) + rr;
+            if (orow >= M) break;
+            for (int cc = lane; cc < CW; cc += 32) {
+              if (col0 + cc >= N) break;
+              const int byte = cc * esz;
+              const uint32_t src = sbuf + stage_off(rr, byte >> 4) + (byte & 15);
+              if (out_bf16) {
+                uint16_t hv;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(src));
+                reinterpret_cast<uint16_t*>(ep.C)[orow * ep.ldc + col0 + cc] = hv;
+              } else {
+                float fv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(fv) : "r"(src));
+                reinterpret_cast<float*>(ep.C)[orow * ep.ldc + col0 + cc] = fv;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        buf ^= 1;
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have completed before the CTA retires
   }
 
   tcgen05_fence_before();
@@ -380,14 +465,15 @@ PFN_tmapEncodeTiled get_encode_fn() {
 
 // 2-D bf16 tensor map: inner extent `cols` (contiguous), `rows` rows with `ld` elements between rows,
 // box = 64 x box_rows, 128-byte swizzle, out-of-bounds reads return zero.
-int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int64_t ld, int box_rows) {
+int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int64_t ld, int box_rows, int box_cols = BLOCK_K,
+              bool f32 = false) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   FDM_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FDM_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld ld=%lld)",
@@ -407,9 +493,15 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   }
   const int taps = a.taps > 1 ? a.taps : 1;
   const int64_t a_cols = taps > 1 ? a.tap_k : a.K;
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_c;
   if (int rc = make_tmap(&tm_a, a.A, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
   if (int rc = make_tmap(&tm_b, a.W, a.K, a.N, a.ldw, BLOCK_N)) return rc;
+  if (ep.tma_c) {
+    const bool f32 = a.out_dtype == FDM_F32;
+    if (int rc = make_tmap(&tm_c, a.C, a.N, a.M, a.ldc, 32, f32 ? 32 : 64, f32)) return rc;
+  } else {
+    tm_c = tm_a;  // unused placeholder (must still be a valid parameter)
+  }
   const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M));
   const int n_tiles = static_cast<int>(ceil_div64(a.N, BLOCK_N));
   const int num_k_blocks = static_cast<int>(ceil_div64(a.K, BLOCK_K));
@@ -417,7 +509,7 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
   const int grid = static_cast<int>(tiles < fdm_sm_count() ? tiles : fdm_sm_count());
   gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(
-      tm_a, tm_b, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
+      tm_a, tm_b, tm_c, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
       taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles);
   FDM_CHECK_LAUNCH();
   return 0;
@@ -449,7 +541,8 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   ep.out_dtype = a.out_dtype;
   ep.act = a.act;
   const int64_t csz = a.out_dtype == FDM_BF16 ? 2 : 4, rsz = a.res_dtype == FDM_BF16 ? 2 : 4;
-  ep.vec_c = aligned16(a.C) && (a.ldc * csz) % 16 == 0;
+  ep.tma_c = aligned16(a.C) && (a.ldc * csz) % 16 == 0;
+  ep.M = static_cast<int32_t>(a.M);
   ep.vec_r = a.residual && aligned16(a.residual) && (a.ldr * rsz) % 16 == 0;
   ep.vec_bias = a.bias && aligned16(a.bias);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
