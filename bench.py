@@ -313,8 +313,8 @@ def main():
         zq, _, _ = ae.quant(lat, emo_dev) if P.emotion else ae.quant(lat)
         verts = ae.decode(zq)
         if world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(gathered.view(-1), verts.view(-1))
+            from fdm_b200.parallel import gather_clips
+            gather_clips(verts, out=gathered)  # the path's only collective: one NCCL all-gather of the vertices
         return verts
 
     def fresh_inputs():
