@@ -42,6 +42,7 @@ struct Epilogue {
   int64_t ldr, ldc;
   int32_t res_dtype, out_dtype, act;
   int32_t tma_c, vec_r, vec_bias;  // C through TMA stores; 16-byte vector access legal for residual / bias
+  int32_t tma_r;                   // bf16 residual tiles fetched by TMA into the staging tile (needs tma_c, bf16 out)
   int32_t M;
 };
 
@@ -254,7 +255,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_c, const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
                const int tap_row_shift, const int m_tiles, const int n_tiles) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -267,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + ACC_STAGES + a); };
+  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 2 * ACC_STAGES + 1 + 2 * w + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5;
@@ -277,6 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (ep.tma_c) tma_prefetch_desc(&tmap_c);
+    if (ep.tma_r) tma_prefetch_desc(&tmap_r);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -285,6 +288,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
+    }
+    for (int w = 0; w < 4; ++w) {
+      mbar_init(res_bar(w, 0), 1);
+      mbar_init(res_bar(w, 1), 1);
     }
     fence_barrier_init();
   } else if (warp == 2) {
@@ -350,6 +357,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int CW = out_bf16 ? 64 : 32;  // output columns per 128-byte staging row
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
+    if (ep.tma_r) {
+      // ---- bf16 out + bf16 residual, both through TMA: the residual chunk is fetched into the staging tile one chunk
+      //      ahead, each thread adds its own row in place, and the same tile is handed to the TMA store engine ----
+      const int ew = warp - 2;
+      uint32_t rphase = 0u;  // bit b = parity of residual barrier b
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int row_w = m_blk * BLOCK_M + quad * 32;
+        const int n_base = n_blk * BLOCK_N;
+        const int n_chunks = min(BLOCK_N / 64, (N - n_base + 63) / 64);
+        if (lane == 0) {
+          bulk_wait_read<1>();  // the store issued two chunks ago (same staging tile) has finished reading it
+          mbar_expect_tx(res_bar(ew, buf), 4096);
+          tma_load_2d(stage_base + buf * 4096u, &tmap_r, res_bar(ew, buf), n_base, row_w);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          const int col0 = n_base + c * 64;
+          const uint32_t sbuf = stage_base + buf * 4096u;
+          if (c + 1 < n_chunks && lane == 0) {
+            bulk_wait_read<0>();  // previous chunk's store has released the other staging tile
+            mbar_expect_tx(res_bar(ew, buf ^ 1), 4096);
+            tma_load_2d(stage_base + (buf ^ 1) * 4096u, &tmap_r, res_bar(ew, buf ^ 1), col0 + 64, row_w);
+          }
+          mbar_wait(res_bar(ew, buf), (rphase >> buf) & 1u);
+          rphase ^= 1u << buf;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (col0 + half * 32 >= N) break;  // warp-uniform
+            uint32_t r[32];
+            float v[32];
+            tmem_ld_32x32b_x32(tacc + c * 64 + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            {  // bias + activation (no residual here)
+              Epilogue e2 = ep;
+              e2.residual = nullptr;
+              epilogue_math(v, e2, 0, false, col0 + half * 32, N);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t addr = sbuf + stage_off(lane, half * 4 + j);
+              uint32_t q0, q1, q2, q3;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(addr));
+              const uint32_t qq[4] = {q0, q1, q2, q3};
+              uint32_t oo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
+                oo[e] = pack2(v[8 * j + 2 * e] + f.x, v[8 * j + 2 * e + 1] + f.y);
+              }
+              st_shared_v4(addr, oo[0], oo[1], oo[2], oo[3]);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, sbuf, col0, row_w);
+            bulk_commit();
+          }
+          buf ^= 1;
+        }
+        tcgen05_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -502,6 +580,10 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   } else {
     tm_c = tm_a;  // unused placeholder (must still be a valid parameter)
   }
+  CUtensorMap tm_r = tm_a;
+  if (ep.tma_r) {
+    if (int rc = make_tmap(&tm_r, a.residual, a.N, a.M, a.ldr, 32, 64, false)) return rc;
+  }
   const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M));
   const int n_tiles = static_cast<int>(ceil_div64(a.N, BLOCK_N));
   const int num_k_blocks = static_cast<int>(ceil_div64(a.K, BLOCK_K));
@@ -509,7 +591,7 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
   const int grid = static_cast<int>(tiles < fdm_sm_count() ? tiles : fdm_sm_count());
   gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(
-      tm_a, tm_b, tm_c, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
+      tm_a, tm_b, tm_c, tm_r, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
       taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles);
   FDM_CHECK_LAUNCH();
   return 0;
@@ -545,6 +627,8 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   ep.M = static_cast<int32_t>(a.M);
   ep.vec_r = a.residual && aligned16(a.residual) && (a.ldr * rsz) % 16 == 0;
   ep.vec_bias = a.bias && aligned16(a.bias);
+  ep.tma_r = ep.tma_c && a.residual && a.res_dtype == FDM_BF16 && a.out_dtype == FDM_BF16 && aligned16(a.residual) &&
+             (a.ldr * 2) % 16 == 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 
   // Tile width: the widest tile that still yields at least one tile per SM; narrow problems fall to 64.

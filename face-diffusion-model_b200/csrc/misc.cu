@@ -71,8 +71,13 @@ __global__ void __launch_bounds__(256) hubert_conv0_kernel(const float* __restri
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 10; ++k) acc = fmaf(ws[c * 10 + k], x[k], acc);
-    v[j] = acc + bias[c];
+    v[j] = acc + (bias ? bias[c] : 0.f);
     s += v[j];
+  }
+  if (g == nullptr) {  // raw conv output: normalised over time by a later kernel (wav2vec2 "group" variant)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) st_from_float(out, od, orow + lane + 32 * j, v[j]);
+    return;
   }
   const float mean = warp_sum(s) / C;
   float q = 0.f;
@@ -124,7 +129,7 @@ extern "C" int fdm_pad_time(const void* src, int64_t src_t_stride, void* dst, in
 extern "C" int fdm_hubert_conv0(const float* audio, int64_t B, int64_t L, const float* w, const float* bias, const float* ln_g,
                                 const float* ln_b, void* out, int32_t out_dtype, int64_t Lout, int64_t out_t_stride, int64_t C,
                                 void* stream) {
-  FDM_CHECK_ARG(audio && w && bias && ln_g && ln_b && out, "fdm_hubert_conv0: null operand");
+  FDM_CHECK_ARG(audio && w && out && ((ln_g == nullptr) == (ln_b == nullptr)), "fdm_hubert_conv0: null operand");
   FDM_CHECK_ARG(B > 0 && B <= 65535 && Lout > 0 && out_t_stride >= Lout && (Lout - 1) * 5 + 10 <= L, "fdm_hubert_conv0: bad sizes");
   dim3 grid(static_cast<unsigned>(ceil_div64(out_t_stride, 8)), static_cast<unsigned>(B));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

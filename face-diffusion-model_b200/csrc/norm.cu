@@ -271,7 +271,7 @@ bool try_fast_ln(const fdm_norm_args& a, cudaStream_t s) {
 // block = 32 channels x 8 time-lanes; grid = (C/32, B)
 __global__ void __launch_bounds__(256) leaky_instnorm_kernel(const void* x, int x_dtype, void* out, int out_dtype, int T,
                                                              int64_t t_stride, int64_t out_t_stride, int C, float slope,
-                                                             float eps) {
+                                                             float eps, const float* gamma, const float* beta, int post_act) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -304,11 +304,14 @@ __global__ void __launch_bounds__(256) leaky_instnorm_kernel(const void* x, int 
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += red[i][cx];
   const float rstd = 1.f / sqrtf(tot / static_cast<float>(T) + eps);
+  const float gm = (gamma && ok) ? gamma[c] : 1.f, bt = (beta && ok) ? beta[c] : 0.f;
   for (int t = ty; t < T; t += 8)
     if (ok) {
       float v = ld_as_float(x, x_dtype, base + static_cast<int64_t>(t) * C + c);
       v = (v > 0.f ? v : slope * v);
-      st_from_float(out, out_dtype, obase + static_cast<int64_t>(t) * C + c, (v - mean) * rstd);
+      v = (v - mean) * rstd * gm + bt;
+      if (post_act == FDM_ACT_GELU_ERF) v = act_gelu_erf(v);
+      st_from_float(out, out_dtype, obase + static_cast<int64_t>(t) * C + c, v);
     }
 }
 
@@ -353,12 +356,14 @@ extern "C" int fdm_layernorm(const fdm_norm_args* args, void* stream) {
 }
 
 extern "C" int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int32_t out_dtype, int64_t B, int64_t T,
-                                  int64_t t_stride, int64_t out_t_stride, int64_t C, float slope, float eps, void* stream) {
+                                  int64_t t_stride, int64_t out_t_stride, int64_t C, float slope, float eps, const float* gamma,
+                                  const float* beta, int32_t post_act, void* stream) {
   FDM_CHECK_ARG(x && out && B > 0 && T > 0 && C > 0 && t_stride >= T && out_t_stride >= T, "fdm_leaky_instnorm: bad arguments");
   FDM_CHECK_ARG(x != out || t_stride == out_t_stride, "fdm_leaky_instnorm: in-place needs equal strides");
+  FDM_CHECK_ARG(post_act == FDM_ACT_NONE || post_act == FDM_ACT_GELU_ERF, "fdm_leaky_instnorm: post_act must be NONE or GELU_ERF");
   dim3 grid(static_cast<unsigned>(ceil_div64(C, 32)), static_cast<unsigned>(B));
   leaky_instnorm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, out, out_dtype, static_cast<int>(T),
-                                                                                  t_stride, out_t_stride, static_cast<int>(C), slope, eps);
+                                                                                  t_stride, out_t_stride, static_cast<int>(C), slope, eps, gamma, beta, post_act);
   FDM_CHECK_LAUNCH();
   return 0;
 }

@@ -30,9 +30,11 @@ class AudioEncoderEngine:
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self._packed_key = None
         cfg = self.cfg
-        if cfg.feat_extract_norm != "layer" or not cfg.do_stable_layer_norm:
-            raise NotImplementedError("only the layer-norm feature encoder + stable-layer-norm encoder "
-                                      "(hubert-large-ls960-ft family) is implemented on the CUDA path")
+        # two architecture families: hubert-large-ls960-ft ("layer" feature-encoder norm, conv bias, pre-LN "stable"
+        # encoder) and wav2vec2-base-960h ("group" norm on the first conv only, no conv bias, post-LN encoder)
+        self.layer_norm_convs = cfg.feat_extract_norm == "layer"
+        self.stable = bool(cfg.do_stable_layer_norm)
+        assert cfg.feat_extract_norm in ("layer", "group")
         assert cfg.conv_kernel[0] == 10 and cfg.conv_stride[0] == 5 and all(s == 2 for s in cfg.conv_stride[1:])
         assert cfg.hidden_act == "gelu" and cfg.feat_extract_activation == "gelu"
 
@@ -49,22 +51,33 @@ class AudioEncoderEngine:
         w = {}
         convs = m.feature_extractor.conv_layers
         c0 = convs[0]
+        opt = lambda t: None if t is None else Fv(t)
         w["c0_w"] = Fv(c0.conv.weight.reshape(c0.conv.weight.shape[0], -1))
-        w["c0_b"], w["c0_g"], w["c0_beta"] = Fv(c0.conv.bias), Fv(c0.layer_norm.weight), Fv(c0.layer_norm.bias)
+        w["c0_b"], w["c0_g"], w["c0_beta"] = opt(c0.conv.bias), Fv(c0.layer_norm.weight), Fv(c0.layer_norm.bias)
         w["convs"] = []
         for layer in convs[1:]:
             cw = layer.conv.weight  # [Cout, Cin, k] -> [Cout, k, Cin] (tap-major K, matching overlapping rows)
-            w["convs"].append(dict(w=W(cw.permute(0, 2, 1).reshape(cw.shape[0], -1)), b=Fv(layer.conv.bias),
-                                   g=Fv(layer.layer_norm.weight), beta=Fv(layer.layer_norm.bias), k=cw.shape[2]))
+            ln = getattr(layer, "layer_norm", None)
+            w["convs"].append(dict(w=W(cw.permute(0, 2, 1).reshape(cw.shape[0], -1)), b=opt(layer.conv.bias),
+                                   g=None if ln is None else Fv(ln.weight), beta=None if ln is None else Fv(ln.bias),
+                                   k=cw.shape[2]))
         fp = m.feature_projection
-        w["fp_g"], w["fp_beta"] = Fv(fp.layer_norm.weight), Fv(fp.layer_norm.bias)
+        has_fp_ln = getattr(fp, "layer_norm", None) is not None and getattr(fp, "feat_proj_layer_norm", True)
+        w["fp_g"], w["fp_beta"] = (Fv(fp.layer_norm.weight), Fv(fp.layer_norm.bias)) if has_fp_ln else (None, None)
         w["fp_w"], w["fp_b"] = W(fp.projection.weight), Fv(fp.projection.bias)
         pc = m.encoder.pos_conv_embed.conv
         pw = pc.weight.detach()  # weight-norm parametrisation resolved by torch: [C, C/groups, k]
         G = cfg.num_conv_pos_embedding_groups
         C = cfg.hidden_size
         cg = C // G
-        w["pos_w"] = [W(pw[g * cg:(g + 1) * cg].permute(0, 2, 1).reshape(cg, -1)) for g in range(G)]
+        # the tcgen05 implicit-conv path needs 64-element taps: pad each group's input channels to a multiple of 64
+        self.cg_pad = cg if (self.dtype == torch.float32 or cg % 64 == 0) else (cg + 63) // 64 * 64
+        w["pos_w"] = []
+        for g in range(G):
+            wg = pw[g * cg:(g + 1) * cg].permute(0, 2, 1)  # [cout, k, cin]
+            if self.cg_pad != cg:
+                wg = torch.nn.functional.pad(wg, (0, self.cg_pad - cg))
+            w["pos_w"].append(W(wg.reshape(cg, -1)))
         w["pos_b"] = [Fv(pc.bias[g * cg:(g + 1) * cg]) for g in range(G)]
         w["layers"] = []
         for lyr in m.encoder.layers:
@@ -104,46 +117,74 @@ class AudioEncoderEngine:
         Cc = cfg.conv_dim[0]
         slack = 2
         cur = torch.zeros(B * strides[0] + slack, Cc, device=dev, dtype=dt)
-        lib.hubert_conv0(audio, w["c0_w"], w["c0_b"], w["c0_g"], w["c0_beta"], cur, lens[0], strides[0], Cc)
+        if self.layer_norm_convs:
+            lib.hubert_conv0(audio, w["c0_w"], w["c0_b"], w["c0_g"], w["c0_beta"], cur, lens[0], strides[0], Cc)
+        else:
+            # conv (no norm) -> per-channel GroupNorm over time (affine) -> GELU; padding rows stay zero
+            lib.hubert_conv0(audio, w["c0_w"], w["c0_b"], None, None, cur, lens[0], strides[0], Cc)
+            lib.leaky_instnorm(cur, cur, B, lens[0], strides[0], Cc, slope=1.0, eps=1e-5, gamma=w["c0_g"], beta=w["c0_beta"],
+                               post_act=lib.ACT_GELU_ERF)
         for i, cv in enumerate(w["convs"], start=1):
             nxt = torch.zeros(B * strides[i] + slack, cfg.conv_dim[i], device=dev, dtype=dt)
             M = B * strides[i]
-            lib.gemm(cur, cv["w"], nxt, bias=cv["b"], M=M, lda=2 * cfg.conv_dim[i - 1], a_rows=M, K=cv["k"] * cfg.conv_dim[i - 1])
-            lib.layernorm(nxt[:M], nxt[:M], g1=cv["g"], b1=cv["beta"], act1=lib.ACT_GELU_ERF)
+            if cv["g"] is not None:
+                lib.gemm(cur, cv["w"], nxt, bias=cv["b"], M=M, lda=2 * cfg.conv_dim[i - 1], a_rows=M, K=cv["k"] * cfg.conv_dim[i - 1])
+                lib.layernorm(nxt[:M], nxt[:M], g1=cv["g"], b1=cv["beta"], act1=lib.ACT_GELU_ERF)
+            else:
+                lib.gemm(cur, cv["w"], nxt, bias=cv["b"], act=lib.ACT_GELU_ERF, M=M, lda=2 * cfg.conv_dim[i - 1], a_rows=M,
+                         K=cv["k"] * cfg.conv_dim[i - 1])
             cur = nxt
-        N = lens[-1] - (lens[-1] % 2)  # models/hubert.py:95-96: drop an odd last frame
+        N = lens[-1] - (lens[-1] % 2)  # models/hubert.py:95-96 / models/wav2vec.py:88-89: drop an odd last frame
         Lp = strides[-1]
         C = cfg.hidden_size
         M = B * Lp
-        lib.layernorm(cur[:M], cur[:M], g1=w["fp_g"], b1=w["fp_beta"], eps=cfg.layer_norm_eps)
+        eps = cfg.layer_norm_eps
+        if w["fp_g"] is not None:
+            lib.layernorm(cur[:M], cur[:M], g1=w["fp_g"], b1=w["fp_beta"], eps=eps)
         hid = torch.empty(M, C, device=dev, dtype=dt)
         lib.gemm(cur[:M], w["fp_w"], hid, bias=w["fp_b"])
         # positional conv embedding: zero padding k/2 both sides, grouped conv as per-tap row-shifted GEMMs
         kpos, G = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
         cg = C // G
+        cgp = self.cg_pad
         pad = kpos // 2
         Tp = (N + 2 * pad + 7) // 8 * 8
         xpad = torch.zeros(B * Tp, C, device=dev, dtype=dt)
         lib.pad_time(hid, xpad, B, N, C, pad, Tp - N - pad, 0, src_t_stride=Lp)
+        if cgp != cg:  # regroup channels so every group starts at a 64-element boundary (zero-filled tail)
+            xg = torch.zeros(B * Tp, G * cgp, device=dev, dtype=dt)
+            xg.view(B * Tp, G, cgp)[:, :, :cg] = xpad.view(B * Tp, G, cg)
+        else:
+            xg = xpad
         x = torch.zeros(B * Tp, C, device=dev, dtype=dt)
         Mp = B * Tp - (kpos - 1)
         for g in range(G):
-            lib.gemm(xpad[:, g * cg:], w["pos_w"][g], x[:, g * cg:(g + 1) * cg], bias=w["pos_b"][g], act=lib.ACT_GELU_ERF,
-                     residual=xpad[pad:, g * cg:(g + 1) * cg], M=Mp, lda=C, a_rows=B * Tp, taps=kpos, tap_k=cg, tap_row_shift=1)
+            lib.gemm(xg[:, g * cgp:], w["pos_w"][g], x[:, g * cg:(g + 1) * cg], bias=w["pos_b"][g], act=lib.ACT_GELU_ERF,
+                     residual=xpad[pad:, g * cg:(g + 1) * cg], M=Mp, lda=G * cgp, a_rows=B * Tp, taps=kpos, tap_k=cgp, tap_row_shift=1)
         H = cfg.num_attention_heads
         dh = C // H
         qkv = torch.empty(B * Tp, 3 * C, device=dev, dtype=dt)
         y = torch.empty(B * Tp, C, device=dev, dtype=dt)
         att = torch.zeros(B * Tp, C, device=dev, dtype=dt)
         ffn = torch.empty(B * Tp, cfg.intermediate_size, device=dev, dtype=dt)
-        eps = cfg.layer_norm_eps
-        for Lw in w["layers"]:
-            lib.layernorm(x, y, g1=Lw["ln1_g"], b1=Lw["ln1_b"], eps=eps)
-            lib.gemm(y, Lw["qkv_w"], qkv, bias=Lw["qkv_b"])
-            lib.self_attention(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, B, N, Tp, H, dh, dh ** -0.5)
-            lib.gemm(att, Lw["o_w"], x, bias=Lw["o_b"], residual=x)
-            lib.layernorm(x, y, g1=Lw["ln2_g"], b1=Lw["ln2_b"], eps=eps)
-            lib.gemm(y, Lw["f1_w"], ffn, bias=Lw["f1_b"], act=lib.ACT_GELU_ERF)
-            lib.gemm(ffn, Lw["f2_w"], x, bias=Lw["f2_b"], residual=x)
-        lib.layernorm(x, y, g1=w["ln_g"], b1=w["ln_b"], eps=eps)
+        if self.stable:
+            for Lw in w["layers"]:  # pre-LN ("stable layer norm") layers, final LayerNorm at the end
+                lib.layernorm(x, y, g1=Lw["ln1_g"], b1=Lw["ln1_b"], eps=eps)
+                lib.gemm(y, Lw["qkv_w"], qkv, bias=Lw["qkv_b"])
+                lib.self_attention(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, B, N, Tp, H, dh, dh ** -0.5)
+                lib.gemm(att, Lw["o_w"], x, bias=Lw["o_b"], residual=x)
+                lib.layernorm(x, y, g1=Lw["ln2_g"], b1=Lw["ln2_b"], eps=eps)
+                lib.gemm(y, Lw["f1_w"], ffn, bias=Lw["f1_b"], act=lib.ACT_GELU_ERF)
+                lib.gemm(ffn, Lw["f2_w"], x, bias=Lw["f2_b"], residual=x)
+            lib.layernorm(x, y, g1=w["ln_g"], b1=w["ln_b"], eps=eps)
+        else:
+            lib.layernorm(x, y, g1=w["ln_g"], b1=w["ln_b"], eps=eps)  # encoder.layer_norm right after the pos-conv add
+            for Lw in w["layers"]:  # post-LN layers
+                lib.gemm(y, Lw["qkv_w"], qkv, bias=Lw["qkv_b"])
+                lib.self_attention(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, B, N, Tp, H, dh, dh ** -0.5)
+                lib.gemm(att, Lw["o_w"], x, bias=Lw["o_b"], residual=y)
+                lib.layernorm(x, y, g1=Lw["ln1_g"], b1=Lw["ln1_b"], eps=eps)
+                lib.gemm(y, Lw["f1_w"], ffn, bias=Lw["f1_b"], act=lib.ACT_GELU_ERF)
+                lib.gemm(ffn, Lw["f2_w"], x, bias=Lw["f2_b"], residual=y)
+                lib.layernorm(x, y, g1=Lw["ln2_g"], b1=Lw["ln2_b"], eps=eps)
         return y.view(B, Tp, C)[:, :N]

@@ -56,7 +56,7 @@ EXPORTS = {
     "fdm_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_layernorm": (C.c_int, [C.POINTER(NormArgs), _vp]),
-    "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
+    "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _i32, _vp]),
     "fdm_self_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "fdm_ddpm_step": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
     "fdm_advance_cursor": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
@@ -206,10 +206,12 @@ def layernorm(x: torch.Tensor, out: torch.Tensor, g1=None, b1=None, r1=None, act
 
 
 def leaky_instnorm(x: torch.Tensor, out: torch.Tensor, B: int, T: int, t_stride: int, Cn: int,
-                   slope: float = 0.2, eps: float = 1e-5, out_t_stride: Optional[int] = None) -> torch.Tensor:
+                   slope: float = 0.2, eps: float = 1e-5, out_t_stride: Optional[int] = None, gamma=None, beta=None,
+                   post_act: int = ACT_NONE) -> torch.Tensor:
     lib = require_device()
     _check(lib.fdm_leaky_instnorm(_ptr(x), _dt(x), _ptr(out), _dt(out), B, T, t_stride,
-                                  out_t_stride if out_t_stride is not None else t_stride, Cn, slope, eps, _stream()))
+                                  out_t_stride if out_t_stride is not None else t_stride, Cn, slope, eps,
+                                  _ptr(gamma), _ptr(beta), post_act, _stream()))
     _launched()
     return out
 

@@ -99,12 +99,16 @@ typedef struct fdm_norm_args {
 } fdm_norm_args;
 int fdm_layernorm(const fdm_norm_args* args, void* stream);
 
-/* LeakyReLU(0.2) + InstanceNorm1d over time (affine=False, eps, biased variance) on a
- * [B, T (t_stride rows per clip), C] activation, written with out_t_stride rows per clip (this also
- * compacts the padded conv output); models/vq_vae_vocaset.py:194-199. */
+/* y = post_act( InstanceNorm_over_time( leaky_relu(x, slope) ) * gamma + beta ) on a [B, T (t_stride rows per
+ * clip), C] activation, written with out_t_stride rows per clip (this also compacts a padded conv output).
+ * slope = 0.2, gamma = beta = NULL, post_act = NONE: LeakyReLU + InstanceNorm1d(affine=False) of the VQ decoder
+ * expander (models/vq_vae_vocaset.py:194-199). slope = 1, gamma/beta, post_act = GELU: the per-channel GroupNorm +
+ * GELU after the first conv of the wav2vec2-base feature encoder (HF Wav2Vec2GroupNormConvLayer, behind
+ * models/wav2vec.py:88). Statistics are biased (divide by T), fp32. */
 int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int32_t out_dtype,
                        int64_t B, int64_t T, int64_t t_stride, int64_t out_t_stride, int64_t C,
-                       float slope, float eps, void* stream);
+                       float slope, float eps, const float* gamma, const float* beta, int32_t post_act,
+                       void* stream);
 
 /* ---- attention ---------------------------------------------------------------- *
  * O[b,t,h,:] = softmax_j( scale * Q[b,t,h,:].K[b,j,h,:] + bias(h,t,j) ) V[b,j,h,:]
@@ -172,7 +176,9 @@ int fdm_transpose_bcl_to_blc(const float* src, void* dst, int32_t dst_dtype,
  * replicated edge rows (mode 1, Conv1d padding_mode='replicate') or zeros (mode 0). */
 int fdm_pad_time(const void* src, int64_t src_t_stride, void* dst, int32_t dtype, int64_t B, int64_t T,
                  int64_t C, int64_t pad_l, int64_t pad_r, int32_t mode, void* stream);
-/* HuBERT conv layer 0: Conv1d(1, C, k=10, stride=5, bias) + LayerNorm(C) + GELU on raw audio.
+/* Audio feature-encoder layer 0: Conv1d(1, C, k=10, stride=5, optional bias) on raw audio, then
+ * LayerNorm(C) + GELU (ln_g != NULL: hubert-large "layer" variant) or nothing (ln_g == NULL: wav2vec2-base "group"
+ * variant, normalised over time afterwards by fdm_leaky_instnorm).
  * audio [B, L] f32 -> out [B, out_t_stride, C] (rows >= Lout zero-filled). */
 int fdm_hubert_conv0(const float* audio, int64_t B, int64_t L, const float* w, const float* bias,
                      const float* ln_g, const float* ln_b, void* out, int32_t out_dtype,

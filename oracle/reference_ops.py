@@ -281,9 +281,9 @@ def audio_encoder_config(kind: str, tiny: bool = False):
                       num_conv_pos_embedding_groups=4)
         return HubertConfig(**kw)
     kw = dict(attn_implementation="eager")  # wav2vec2-base-960h defaults
-    if tiny:
+    if tiny:  # keeps 16 positional-conv groups (48 channels each): the channel-padding path of the CUDA encoder
         kw.update(num_hidden_layers=2, intermediate_size=256, conv_dim=(32,) * 7, num_conv_pos_embeddings=16,
-                  num_conv_pos_embedding_groups=4)
+                  num_conv_pos_embedding_groups=16)
     return Wav2Vec2Config(**kw)
 
 

@@ -56,6 +56,26 @@ def test_gemm_bf16_epilogue(cuda_dev, act):
         assert _rel(out, fns[act](a.float() @ w.float().t() + bias) + res_t.float()) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 512), (130, 200, 64), (1000, 3072, 1024), (128, 64, 128)])
+def test_gemm_bf16_out_with_bf16_residual_tma_path(cuda_dev, M, N, K):
+    """bf16 output + bf16 residual: both move through TMA (staging tile); includes the in-place x = x + f(x) form."""
+    from fdm_b200 import lib
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev).bfloat16()
+    ref = torch.relu(a.float() @ w.float().t() + bias) + res.float()
+    out = torch.full((M, N), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    lib.gemm(a, w, out, bias=bias, act=lib.ACT_RELU, residual=res)
+    x = res.clone()
+    lib.gemm(a, w, x, bias=bias, act=lib.ACT_RELU, residual=x)  # in place
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 6e-3
+    assert torch.equal(out, x)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gemm_implicit_conv(cuda_dev, dtype):
     """Conv1d(k=5, pad=2 replicate) and a stride-2 k=3 conv as shifted-row / overlapping-row GEMMs."""

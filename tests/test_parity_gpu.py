@@ -10,7 +10,7 @@ from helpers import N_SAMPLES, build_product, golden, hf_audio_model, oracle_inp
 
 pytestmark = pytest.mark.gpu
 PRESETS = ["vocaset", "mead", "biwi"]
-HAS_CUDA_AUDIO = {"vocaset": True, "mead": True, "biwi": False}  # wav2vec2-base encoder: injected features
+HAS_CUDA_AUDIO = {"vocaset": True, "mead": True, "biwi": True}
 
 
 def _rel(a, b):
@@ -44,7 +44,7 @@ def _conds(P, idh, emo):
     return (emo, idh) if P["emotion"] else (idh,)
 
 
-@pytest.mark.parametrize("preset", ["vocaset", "mead"])
+@pytest.mark.parametrize("preset", PRESETS)
 def test_audio_encoder_fp32(cuda_dev, preset):
     fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup(preset, cuda_dev, "fp32")
     g = golden(preset)
@@ -98,6 +98,13 @@ def test_chain_quant_decode_fp32(cuda_dev, preset, graph):
         v = verts[0].cpu().numpy()
         lve = lip_vertex_error(np.zeros_like(v), v, lip)
         assert abs(lve - float(g["lve_reference"])) <= 0.01 * float(g["lve_reference"])
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_audio_encoder_bf16(cuda_dev, preset):
+    fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup(preset, cuda_dev, "bf16")
+    got = fdm.encode_audio(audio)[0].float().cpu()
+    assert _rel(got, hiddens[0]) < 3e-2
 
 
 @pytest.mark.parametrize("preset", PRESETS)
