@@ -88,6 +88,38 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, c
   }
 }
 
+__global__ void __launch_bounds__(256) ddim_step_kernel(const fdm_ddim_args a, const int64_t n4) {
+  const int i0 = *a.index_dev;
+  const float A = a.a_recip[i0], Bm = a.a_recipm1[i0], sa = a.sqrt_an[i0], c = a.c[i0];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 x0 = reinterpret_cast<const float4*>(a.x0_cond)[i];
+    if (a.x0_uncond) {
+      const float4 u = reinterpret_cast<const float4*>(a.x0_uncond)[i];
+      x0.x = __fadd_rn(u.x, __fmul_rn(a.guidance, __fsub_rn(x0.x, u.x)));
+      x0.y = __fadd_rn(u.y, __fmul_rn(a.guidance, __fsub_rn(x0.y, u.y)));
+      x0.z = __fadd_rn(u.z, __fmul_rn(a.guidance, __fsub_rn(x0.z, u.z)));
+      x0.w = __fadd_rn(u.w, __fmul_rn(a.guidance, __fsub_rn(x0.w, u.w)));
+    }
+    const float4 xt = reinterpret_cast<const float4*>(a.x_t)[i];
+    float4 o;
+#define FDM_DDIM(X0, XT) __fadd_rn(__fmul_rn(X0, sa), __fmul_rn(c, __fdiv_rn(__fsub_rn(__fmul_rn(A, XT), X0), Bm)))
+    o.x = FDM_DDIM(x0.x, xt.x);
+    o.y = FDM_DDIM(x0.y, xt.y);
+    o.z = FDM_DDIM(x0.z, xt.z);
+    o.w = FDM_DDIM(x0.w, xt.w);
+#undef FDM_DDIM
+    reinterpret_cast<float4*>(a.out)[i] = o;
+    if (a.out_bf16) {
+      uint2 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+      h[0] = __floats2bfloat162_rn(o.x, o.y);
+      h[1] = __floats2bfloat162_rn(o.z, o.w);
+      reinterpret_cast<uint2*>(a.out_bf16)[i] = u;
+    }
+  }
+}
+
 __global__ void advance_cursor_kernel(int32_t* cursor, const int32_t* sched, int n, int32_t* t_dev) {
   const int c = *cursor + 1;
   *cursor = c;
@@ -124,6 +156,19 @@ extern "C" int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream) {
   FDM_CHECK_ARG(al % 16 == 0 && reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0, "fdm_ddpm_step: operands must be 16-byte aligned");
   const int64_t n4 = a.B * a.elems_per_clip / 4;
   ddpm_step_kernel<<<grid_for(n4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, n4, a.elems_per_clip / 4);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_ddim_step(const fdm_ddim_args* args, void* stream) {
+  FDM_CHECK_ARG(args != nullptr, "fdm_ddim_step: null args");
+  const fdm_ddim_args& a = *args;
+  FDM_CHECK_ARG(a.x0_cond && a.x_t && a.out && a.a_recip && a.a_recipm1 && a.sqrt_an && a.c && a.index_dev, "fdm_ddim_step: null operand");
+  FDM_CHECK_ARG(a.n > 0 && a.n % 4 == 0, "fdm_ddim_step: n must be a positive multiple of 4");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a.x0_cond) | reinterpret_cast<uintptr_t>(a.x0_uncond) |
+                       reinterpret_cast<uintptr_t>(a.x_t) | reinterpret_cast<uintptr_t>(a.out);
+  FDM_CHECK_ARG(al % 16 == 0 && reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0, "fdm_ddim_step: operands must be 16-byte aligned");
+  ddim_step_kernel<<<grid_for(a.n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, a.n / 4);
   FDM_CHECK_LAUNCH();
   return 0;
 }

@@ -49,6 +49,11 @@ class DdpmArgs(C.Structure):
                 ("clip_index0", _i64)]
 
 
+class DdimArgs(C.Structure):
+    _fields_ = [("x0_cond", _vp), ("x0_uncond", _vp), ("guidance", _f32), ("x_t", _vp), ("out", _vp), ("out_bf16", _vp),
+                ("a_recip", _vp), ("a_recipm1", _vp), ("sqrt_an", _vp), ("c", _vp), ("index_dev", _vp), ("n", _i64)]
+
+
 EXPORTS = {
     "fdm_last_error": (C.c_char_p, []),
     "fdm_device_info": (C.c_int, [C.POINTER(_i32)] * 3),
@@ -59,6 +64,7 @@ EXPORTS = {
     "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _i32, _vp]),
     "fdm_self_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "fdm_ddpm_step": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
+    "fdm_ddim_step": (C.c_int, [C.POINTER(DdimArgs), _vp]),
     "fdm_advance_cursor": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "fdm_philox_normal": (C.c_int, [_vp, _i64, _i64, _u64, _i64, _i32, _vp]),
     "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
@@ -251,6 +257,22 @@ def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: flo
     a.B, a.elems_per_clip = B, x_t.numel() // B
     a.seed, a.clip_index0 = seed, clip_index0
     _check(lib.fdm_ddpm_step(C.byref(a), _stream()))
+    _launched()
+    return out
+
+
+def ddim_step(x0_cond, x_t, out, a_recip, a_recipm1, sqrt_an, c, index_dev, *, x0_uncond=None, guidance: float = 0.0,
+              out_bf16=None) -> torch.Tensor:
+    lib = require_device()
+    a = DdimArgs()
+    for t in (x0_cond, x_t, out, x0_uncond):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == x_t.numel())
+    a.x0_cond, a.x0_uncond, a.guidance = _ptr(x0_cond), _ptr(x0_uncond), guidance
+    a.x_t, a.out, a.out_bf16 = _ptr(x_t), _ptr(out), _ptr(out_bf16)
+    a.a_recip, a.a_recipm1, a.sqrt_an, a.c = _ptr(a_recip), _ptr(a_recipm1), _ptr(sqrt_an), _ptr(c)
+    assert index_dev.dtype == torch.int32
+    a.index_dev, a.n = _ptr(index_dev), x_t.numel()
+    _check(lib.fdm_ddim_step(C.byref(a), _stream()))
     _launched()
     return out
 

@@ -354,6 +354,40 @@ class GaussianDiffusionBase(nn.Module):
         return out
 
     @torch.inference_mode()
+    def ddim_sample(self, audio, latent_motion_shape, *conds_and_steps, x_T: Optional[torch.Tensor] = None, tap=None):
+        """Deterministic DDIM sampling, eta = 0 (reference diffusion_BIWI_encoder_decoder.py:675-710):
+        ddim_sample(audio, shape, id_one_hot, steps=500). The reference's last time pair (t, -1) evaluates the
+        denoiser and then leaves the sample unchanged; that evaluation is skipped here."""
+        import numpy as np
+        n_c = self.n_cond
+        conds = conds_and_steps[:n_c]
+        n_steps = conds_and_steps[n_c] if len(conds_and_steps) > n_c else 500
+        device = self.betas.device
+        idh, emo = self._split(conds)
+        fdm, level, gcond = self._fdm()
+        P = fdm.preset
+        times = list(reversed(np.linspace(-1, 1000 - 1, n_steps + 1).astype(np.int32).tolist()))
+        pairs = [(i, j) for i, j in zip(times[:-1], times[1:]) if j >= 0]
+        t_cur = torch.tensor([p[0] for p in pairs], dtype=torch.long)
+        t_nxt = torch.tensor([p[1] for p in pairs], dtype=torch.long)
+        # per-step coefficients with the reference's own fp32 expressions, evaluated once on the host
+        ac = self.alphas_cumprod.detach().cpu()
+        a, an = ac[t_cur], ac[t_nxt]
+        sigma = 0.0 * torch.sqrt((1 - a) / (1 - an)) * torch.sqrt(1 - a / an)
+        tables = {"a_recip": self.sqrt_recip_alphas_cumprod.detach().cpu()[t_cur],
+                  "a_recipm1": self.sqrt_recipm1_alphas_cumprod.detach().cpu()[t_cur],
+                  "sqrt_an": torch.sqrt(an), "c": torch.sqrt(1 - an - sigma ** 2)}
+        tables = {k: v.to(device=device, dtype=torch.float32).contiguous() for k, v in tables.items()}
+        shape = tuple(latent_motion_shape)
+        x_T = self._initial_latent(shape, device) if x_T is None else x_T.to(device, torch.float32)
+        eng = fdm.prepare(audio, shape[1] // P.fq, idh, emo, guidance=gcond)
+        sampler = SamplerEngine(eng, self.posterior_mean_coef1, self.posterior_mean_coef2, self._sigma_table(), level)
+        out = sampler.run(x_T, [p[0] for p in pairs], graph=self.use_cuda_graph, tap=tap, ddim=tables,
+                          time_steps=getattr(self, "time_steps", False))
+        self.last_step_ms = sampler.last_step_ms
+        return out
+
+    @torch.inference_mode()
     def sample(self, audio, latent_motion_shape, *conds, **kw):
         return self.p_sample_loop(latent_motion_shape, audio, *conds, **kw)
 

@@ -29,10 +29,12 @@ class SamplerEngine:
     @torch.no_grad()
     def run(self, x_T: torch.Tensor, steps: Sequence[int], noise: NoiseSpec = "philox", seed: int = 0,
             clip_index0: int = 0, graph: bool = True, tap: Optional[Callable[[int, torch.Tensor], None]] = None,
-            time_steps: bool = False) -> torch.Tensor:
+            time_steps: bool = False, ddim: Optional[dict] = None) -> torch.Tensor:
         """x_T (B, fq*T, zdim) fp32 on device; steps: the t values in execution order (e.g. 999..0).
         noise: "philox" (in-kernel counter-based generator), or a callable t -> tensor (host- or device-side,
-        same shape as x_T) that is copied in before every step with t > 0 (parity runs)."""
+        same shape as x_T) that is copied in before every step with t > 0 (parity runs).
+        ddim: None for the ancestral (DDPM) update, or per-step device tables {a_recip, a_recipm1, sqrt_an, c} (one
+        entry per element of `steps`) for the deterministic DDIM update (eta = 0, no noise)."""
         den = self.den
         B, T, d, S = den.B, den.T, den.P.d, den.passes
         assert x_T.is_cuda and x_T.dtype == torch.float32 and x_T.numel() == B * T * d, "x_T does not match prepare()"
@@ -45,15 +47,20 @@ class SamplerEngine:
         sched = torch.tensor(steps, dtype=torch.int32, device=dev)
         cursor = torch.zeros(1, dtype=torch.int32, device=dev)
         t_dev = sched[:1].clone()
-        host_noise = callable(noise)
+        host_noise = callable(noise) and ddim is None
         noise_buf = torch.empty_like(x) if host_noise else None
-        assert host_noise or noise in (None, "philox")
+        assert host_noise or ddim is not None or noise in (None, "philox")
 
         def step_body():
             x0 = den.denoise(xin, t_dev)
-            lib.ddpm_step(x0[0], x, x, self.c1, self.c2, self.sigma, x0_uncond=x0[1] if S == 2 else None,
-                          guidance=float(self.level) if S == 2 else 0.0, noise=noise_buf, out_bf16=xin_bf, t_dev=t_dev,
-                          seed=seed, clip_index0=clip_index0)
+            if ddim is None:
+                lib.ddpm_step(x0[0], x, x, self.c1, self.c2, self.sigma, x0_uncond=x0[1] if S == 2 else None,
+                              guidance=float(self.level) if S == 2 else 0.0, noise=noise_buf, out_bf16=xin_bf, t_dev=t_dev,
+                              seed=seed, clip_index0=clip_index0)
+            else:
+                lib.ddim_step(x0[0], x, x, ddim["a_recip"], ddim["a_recipm1"], ddim["sqrt_an"], ddim["c"], cursor,
+                              x0_uncond=x0[1] if S == 2 else None, guidance=float(self.level) if S == 2 else 0.0,
+                              out_bf16=xin_bf)
             lib.advance_cursor(cursor, sched, t_dev)
 
         def reset():

@@ -149,6 +149,21 @@ typedef struct fdm_ddpm_args {
   uint64_t seed; int64_t clip_index0;
 } fdm_ddpm_args;
 int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream);
+/* DDIM update (eta = 0), reference diffusion_BIWI_encoder_decoder.py:675-710, fused with the optional CFG combine:
+ *   eps = (a_recip[i] * x_t - x0) / a_recipm1[i] ;  out = x0 * sqrt_an[i] + c[i] * eps
+ * where i = *index_dev indexes per-step coefficient tables prepared on the host with the reference's fp32 torch
+ * expressions (a_recip = sqrt_recip_alphas_cumprod[t], a_recipm1 = sqrt_recipm1_alphas_cumprod[t],
+ * sqrt_an = sqrt(alphas_cumprod[t_next]), c = sqrt(1 - alphas_cumprod[t_next])). Each operation is rounded
+ * separately, as in the PyTorch expression. */
+typedef struct fdm_ddim_args {
+  const float* x0_cond; const float* x0_uncond; float guidance;
+  const float* x_t; float* out; void* out_bf16;
+  const float* a_recip; const float* a_recipm1; const float* sqrt_an; const float* c;
+  const int32_t* index_dev;
+  int64_t n;               /* total elements */
+} fdm_ddim_args;
+int fdm_ddim_step(const fdm_ddim_args* args, void* stream);
+
 /* End of a graph-replayed step: cursor[0] += 1; t_dev[0] = t_sched[min(cursor[0], n_sched-1)]. */
 int fdm_advance_cursor(int32_t* cursor_dev, const int32_t* t_sched, int32_t n_sched, int32_t* t_dev, void* stream);
 /* Fill out[B*elems_per_clip] with the same Philox normals the fused step would draw for step t. */

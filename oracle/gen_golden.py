@@ -173,6 +173,23 @@ def main():
         close(xo, xr[0], 2e-5, "6-step p_sample chain")
         g["chain_steps"] = np.array(steps)
         g["chain_out"] = xr[0].numpy()
+        # DDIM (the sampler the shipped VOCASET / BIWI scripts call); x_T injected through torch.randn
+        if preset != "mead":
+            real_randn = torch.randn
+            n_ddim = 6
+            try:
+                if preset == "biwi":
+                    torch.randn = lambda *a, **k: x.reshape(1, T, -1).clone()
+                    dd = diff.ddim_sample(audio, (1, T, P["d"]), idh, n_ddim).reshape(1, T * P["fq"], P["zdim"])
+                else:
+                    torch.randn = lambda *a, **k: x.clone()
+                    dd = diff.ddim_sample(audio, tuple(x.shape), idh, n_ddim)
+            finally:
+                torch.randn = real_randn
+            ddo = R.ddim_sample(tabs, lambda z, t: R.fdm_forward(fsd, preset, hidden[0], t, z, idh, emo), x[0], n_ddim)
+            close(ddo, dd[0], 2e-5, "6-step ddim_sample")
+            g["ddim_steps"] = np.int64(n_ddim)
+            g["ddim_out"] = dd[0].numpy()
         # quantise + decode
         emo_pos = int(torch.argmax(emo)) if P["emotion"] else None
         for cb_kind in ("reference", "normal"):

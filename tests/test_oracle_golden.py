@@ -38,6 +38,18 @@ def test_oracle_fdm_and_chain(preset):
     assert np.abs(out.numpy() - g["chain_out"]).max() < 2e-5
 
 
+@pytest.mark.parametrize("preset", ["vocaset", "biwi"])
+def test_oracle_ddim(preset):
+    from oracle import reference_ops as R
+    g = golden(preset)
+    fdm, ae, diff = build_product(preset)
+    sd, audio, idh, emo = oracle_inputs(preset, fdm)
+    hidden = torch.from_numpy(g["audio_hidden"])
+    x = torch.from_numpy(g["x_T"])
+    out = R.ddim_sample(R.diffusion_tables(1000), lambda z, t: R.fdm_forward(sd, preset, hidden, t, z, idh, emo), x, int(g["ddim_steps"]))
+    assert np.abs(out.numpy() - g["ddim_out"]).max() < 2e-5
+
+
 @pytest.mark.parametrize("preset", PRESETS)
 @pytest.mark.parametrize("codebook", ["reference", "normal"])
 def test_oracle_vq_and_decode(preset, codebook):

@@ -100,6 +100,17 @@ def test_chain_quant_decode_fp32(cuda_dev, preset, graph):
         assert abs(lve - float(g["lve_reference"])) <= 0.01 * float(g["lve_reference"])
 
 
+@pytest.mark.parametrize("preset", ["vocaset", "biwi"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_ddim_sample_fp32(cuda_dev, preset, graph):
+    fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup(preset, cuda_dev, "fp32")
+    g = golden(preset)
+    x = torch.from_numpy(g["x_T"])[None].to(cuda_dev)
+    diff.use_cuda_graph = graph
+    out = diff.ddim_sample(audio, tuple(x.shape), idh, int(g["ddim_steps"]), x_T=x)
+    assert np.abs(out[0].cpu().numpy() - g["ddim_out"]).max() < 1e-4
+
+
 @pytest.mark.parametrize("preset", PRESETS)
 def test_audio_encoder_bf16(cuda_dev, preset):
     fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup(preset, cuda_dev, "bf16")
