@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -26,6 +27,15 @@ int fdm_sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool fdm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FDM_B200_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured no gain (the step is power-capped, not launch-bound)
+  }
+  return v == 1;
 }
 
 extern "C" int fdm_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(THREADS, 3) attn_mma_kernel(const fdm_attn_arg
   const int tabn = T + 64;  // entry k <-> delta = (T - 1) - k, delta in [-64, T-1]
 
   const TileLoader<DH> tl;
+  pdl_trigger();
+  pdl_wait();
   tl.load(s0 + 2 * TILE, Qg, a.ldq, q0, T);
   tl.load(s0, Kg, a.ldk, 0, T);
   tl.load(s0 + TILE, Vg, a.ldv, 0, T);
@@ -299,8 +301,7 @@ int launch(const fdm_attn_args& a, cudaStream_t stream) {
     attr = true;
   }
   dim3 grid(static_cast<unsigned>(ceil_div64(a.T, QB)), static_cast<unsigned>(a.H), static_cast<unsigned>(a.B));
-  attn_mma_kernel<DH, CAUSAL><<<grid, THREADS, smem, stream>>>(a);
-  FDM_CHECK_LAUNCH();
+  FDM_CHECK_CUDA(fdm_launch_pdl(attn_mma_kernel<DH, CAUSAL>, grid, dim3(THREADS), smem, stream, 1, a));
   return 0;
 }
 

@@ -31,6 +31,42 @@ void fdm_set_error(const char* fmt, ...);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int fdm_sm_count();  // cached multiprocessor count of the current device
+bool fdm_pdl_enabled();  // programmatic dependent launch for the hot-loop kernels (opt-in: env FDM_B200_PDL=1)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Hot-loop kernels are launched with programmaticStreamSerialization: kernel N+1 may be scheduled while kernel N
+// drains, runs its prologue (barrier init, TMEM alloc, descriptor prefetch, index math) and then blocks in
+// pdl_wait() until kernel N has completed and its memory is visible. Every kernel launched this way calls
+// pdl_wait() before its first dependent global access; pdl_trigger() lets the next kernel's launch proceed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t fdm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (fdm_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {  // thread-block cluster (CTA pair for tcgen05 cta_group::2)
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- dtype-generic loads / stores (fp32 math everywhere) --------------------------------------
 __device__ __forceinline__ float ld_as_float(const void* p, int32_t dtype, int64_t i) {

@@ -46,6 +46,8 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t clip, u
 }
 
 __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, const int64_t n4, const int64_t e4_per_clip) {
+  pdl_trigger();
+  pdl_wait();
   const int t_graph = a.t_per_clip ? 0 : *a.t_dev;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, c
 }
 
 __global__ void __launch_bounds__(256) ddim_step_kernel(const fdm_ddim_args a, const int64_t n4) {
+  pdl_trigger();
+  pdl_wait();
   const int i0 = *a.index_dev;
   const float A = a.a_recip[i0], Bm = a.a_recipm1[i0], sa = a.sqrt_an[i0], c = a.c[i0];
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -121,6 +125,8 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const fdm_ddim_args a, c
 }
 
 __global__ void advance_cursor_kernel(int32_t* cursor, const int32_t* sched, int n, int32_t* t_dev) {
+  pdl_trigger();
+  pdl_wait();
   const int c = *cursor + 1;
   *cursor = c;
   *t_dev = sched[c < n ? c : n - 1];
@@ -155,8 +161,8 @@ extern "C" int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream) {
                        reinterpret_cast<uintptr_t>(a.out);
   FDM_CHECK_ARG(al % 16 == 0 && reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0, "fdm_ddpm_step: operands must be 16-byte aligned");
   const int64_t n4 = a.B * a.elems_per_clip / 4;
-  ddpm_step_kernel<<<grid_for(n4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, n4, a.elems_per_clip / 4);
-  FDM_CHECK_LAUNCH();
+  FDM_CHECK_CUDA(fdm_launch_pdl(ddpm_step_kernel, dim3(grid_for(n4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, a, n4,
+                                a.elems_per_clip / 4));
   return 0;
 }
 
@@ -168,15 +174,15 @@ extern "C" int fdm_ddim_step(const fdm_ddim_args* args, void* stream) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(a.x0_cond) | reinterpret_cast<uintptr_t>(a.x0_uncond) |
                        reinterpret_cast<uintptr_t>(a.x_t) | reinterpret_cast<uintptr_t>(a.out);
   FDM_CHECK_ARG(al % 16 == 0 && reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0, "fdm_ddim_step: operands must be 16-byte aligned");
-  ddim_step_kernel<<<grid_for(a.n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, a.n / 4);
-  FDM_CHECK_LAUNCH();
+  FDM_CHECK_CUDA(fdm_launch_pdl(ddim_step_kernel, dim3(grid_for(a.n / 4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, a,
+                                a.n / 4));
   return 0;
 }
 
 extern "C" int fdm_advance_cursor(int32_t* cursor_dev, const int32_t* t_sched, int32_t n_sched, int32_t* t_dev, void* stream) {
   FDM_CHECK_ARG(cursor_dev && t_sched && t_dev && n_sched > 0, "fdm_advance_cursor: bad arguments");
-  advance_cursor_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cursor_dev, t_sched, n_sched, t_dev);
-  FDM_CHECK_LAUNCH();
+  FDM_CHECK_CUDA(fdm_launch_pdl(advance_cursor_kernel, dim3(1), dim3(1), 0, reinterpret_cast<cudaStream_t>(stream), 1, cursor_dev, t_sched,
+                                static_cast<int>(n_sched), t_dev));
   return 0;
 }
 

@@ -14,6 +14,7 @@
 // Pipelines: full/empty mbarriers (TMA <-> MMA), tmem_full/tmem_empty mbarriers (MMA <-> epilogue).
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -23,12 +24,17 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int ACC_STAGES = 2;
 
-template <int BLOCK_N>
+// CG = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
+// CG = 2: a CTA pair (cluster of 2 SMs) per 256 x BLOCK_N tile (cta_group::2): each CTA stages its own 128 rows of A and
+//         HALF of the W tile; one MMA issued by the leader CTA reads both CTAs' shared memory and writes both CTAs'
+//         TMEM. Per output element that halves the W traffic from L2 and shared memory and deepens the ring
+//         (6 stages instead of 4) - the GEMMs are power-capped, so fewer bytes moved is more FLOP/s.
+template <int BLOCK_N, int CG = 1>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int STAGES = (BLOCK_N / CG) == 256 ? 4 : ((BLOCK_N / CG) == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int BAR_BYTES = 1024;                  // barriers + TMEM slot, keeps the staging tiles 1024-aligned
   static constexpr int STAGING_BYTES = 4 * 2 * 4096;      // 4 epilogue warps x 2 tiles x (32 rows x 128 B)
@@ -96,6 +102,52 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// ---- cta_group::2 (CTA pair) variants -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; completes on the LEADER CTA's mbarrier (peer bit masked off)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: arrive (once the MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -252,12 +304,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
                const int tap_row_shift, const int m_tiles, const int n_tiles) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -273,7 +325,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = m_tiles * n_tiles;                 // tiles of (128 * CG) x BLOCK_N
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  const int row_in_tile = static_cast<int>(cta_rank) * BLOCK_M;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -282,12 +337,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ep.tma_r) tma_prefetch_desc(&tmap_r);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CG);  // CG = 2: leader's expect_tx arrival + the peer's remote arrival
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 128 * CG);  // epilogue threads of both CTAs arrive on the leader's barrier
     }
     for (int w = 0; w < 4; ++w) {
       mbar_init(res_bar(w, 0), 1);
@@ -295,39 +350,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     fence_barrier_init();
   } else if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+    if (CG == 2) tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands are valid from here on
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int a_row = m_blk * (BLOCK_M * CG) + row_in_tile;
+        const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const int tap = kb / kb_per_tap;
           const int kc = kb - tap * kb_per_tap;
           const uint32_t sa = base + stage * C::STAGE_BYTES;
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kc * BLOCK_K, m_blk * BLOCK_M + tap * tap_row_shift);
-          tma_load_2d(sa + C::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          if (CG == 1) {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
+            tma_load_2d(sa + C::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+          } else {
+            // both CTAs' bytes complete on the leader's barrier; the leader posts the whole transaction count
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
+            tma_load_2d_2sm(sa + C::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+            if (cta_rank != 0) mbar_arrive_remote(full_bar(stage), 0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {
+      // ===== MMA issuer (leader CTA only when CG = 2) =====
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -340,12 +408,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-            umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs when CG = 2) once these MMAs retire
+          if (CG == 2) umma_commit_2sm(empty_bar(stage));
+          else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs when CG = 2)
+        if (CG == 2) umma_commit_2sm(tfull_bar(acc));
+        else umma_commit(tfull_bar(acc));
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -362,9 +435,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       //      ahead, each thread adds its own row in place, and the same tile is handed to the TMA store engine ----
       const int ew = warp - 2;
       uint32_t rphase = 0u;  // bit b = parity of residual barrier b
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-        const int row_w = m_blk * BLOCK_M + quad * 32;
+        const int row_w = m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32;
         const int n_base = n_blk * BLOCK_N;
         const int n_chunks = min(BLOCK_N / 64, (N - n_base + 63) / 64);
         if (lane == 0) {
@@ -424,15 +497,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           buf ^= 1;
         }
         tcgen05_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        if (CG == 2) mbar_arrive_remote(tempty_bar(acc), 0);
+        else mbar_arrive(tempty_bar(acc));
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const int row_w = m_blk * BLOCK_M + quad * 32;  // first row of this warp's slab
+      const int row_w = m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32;  // first row of this warp's slab
       const int64_t row = static_cast<int64_t>(row_w) + lane;
       const bool row_ok = row < M;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
@@ -510,17 +584,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         buf ^= 1;
       }
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (CG == 2) mbar_arrive_remote(tempty_bar(acc), 0);
+      else mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have completed before the CTA retires
   }
 
+  pdl_trigger();  // this CTA's tiles are done: the next kernel's CTAs may start their prologue on freed SMs
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // no CTA of the pair exits while its partner may still signal it
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -561,19 +639,19 @@ int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG = 1>
 int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int taps = a.taps > 1 ? a.taps : 1;
   const int64_t a_cols = taps > 1 ? a.tap_k : a.K;
   CUtensorMap tm_a, tm_b, tm_c;
   if (int rc = make_tmap(&tm_a, a.A, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
-  if (int rc = make_tmap(&tm_b, a.W, a.K, a.N, a.ldw, BLOCK_N)) return rc;
+  if (int rc = make_tmap(&tm_b, a.W, a.K, a.N, a.ldw, BLOCK_N / CG)) return rc;
   if (ep.tma_c) {
     const bool f32 = a.out_dtype == FDM_F32;
     if (int rc = make_tmap(&tm_c, a.C, a.N, a.M, a.ldc, 32, f32 ? 32 : 64, f32)) return rc;
@@ -584,16 +662,16 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   if (ep.tma_r) {
     if (int rc = make_tmap(&tm_r, a.residual, a.N, a.M, a.ldr, 32, 64, false)) return rc;
   }
-  const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M));
+  const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M * CG));
   const int n_tiles = static_cast<int>(ceil_div64(a.N, BLOCK_N));
   const int num_k_blocks = static_cast<int>(ceil_div64(a.K, BLOCK_K));
   const int kb_per_tap = taps > 1 ? static_cast<int>(a.tap_k / BLOCK_K) : num_k_blocks;
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
-  const int grid = static_cast<int>(tiles < fdm_sm_count() ? tiles : fdm_sm_count());
-  gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(
-      tm_a, tm_b, tm_c, tm_r, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
-      taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles);
-  FDM_CHECK_LAUNCH();
+  const int64_t slots = fdm_sm_count() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
+  const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
+  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
+                                tm_c, tm_r, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
+                                taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles));
   return 0;
 }
 
@@ -634,6 +712,10 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   // Tile width: the widest tile that still yields at least one tile per SM; narrow problems fall to 64.
   const int64_t m_tiles = ceil_div64(a.M, BLOCK_M);
   const int sms = fdm_sm_count();
+  // CTA-pair kernel (256 x 256 tiles) whenever there is at least one tile per SM pair and C can go through TMA
+  static const bool two_cta = [] { const char* e = getenv("FDM_B200_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+  if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2)
+    return launch<256, 2>(a, ep, s);
   if (a.N >= 256 && m_tiles * ceil_div64(a.N, 256) >= sms) return launch<256>(a, ep, s);
   if (a.N >= 128 && m_tiles * ceil_div64(a.N, 128) >= sms) return launch<128>(a, ep, s);
   if (a.N > 64 && a.N % 64 != 0 && a.N >= 128) return launch<128>(a, ep, s);

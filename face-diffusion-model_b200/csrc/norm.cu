@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args
   constexpr int NCH = EPL / CE;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5)) * 2;
+  pdl_trigger();
+  pdl_wait();
   if (row0 >= a.rows) return;
   const bool two = row0 + 1 < a.rows;
   const int64_t rows[2] = {row0, two ? row0 + 1 : row0};
@@ -262,10 +264,9 @@ __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args
 template <typename T>
 bool try_fast_ln(const fdm_norm_args& a, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, 8));
-  if (a.d == 1024) layernorm_fast_kernel<T, 32><<<grid, 128, 0, s>>>(a);
-  else if (a.d == 512) layernorm_fast_kernel<T, 16><<<grid, 128, 0, s>>>(a);
-  else return false;
-  return true;
+  if (a.d == 1024) return fdm_launch_pdl(layernorm_fast_kernel<T, 32>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+  if (a.d == 512) return fdm_launch_pdl(layernorm_fast_kernel<T, 16>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+  return false;
 }
 
 // block = 32 channels x 8 time-lanes; grid = (C/32, B)

@@ -15,6 +15,7 @@ GEMM_SHAPES = [
     # M, N, K
     (128, 256, 64), (256, 256, 128), (200, 1024, 1024), (198, 3072, 1024), (792, 1024, 2048),
     (1000, 512, 512), (130, 64, 64), (257, 192, 320), (12672, 1024, 1024), (333, 15069, 1024),
+    (5000, 2048, 512), (4099, 1280, 192), (25344, 3072, 1024),  # CTA-pair (cta_group::2) kernel, with M / N / K tails
 ]
 
 
@@ -56,7 +57,8 @@ def test_gemm_bf16_epilogue(cuda_dev, act):
         assert _rel(out, fns[act](a.float() @ w.float().t() + bias) + res_t.float()) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 1024, 512), (130, 200, 64), (1000, 3072, 1024), (128, 64, 128)])
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 512), (130, 200, 64), (1000, 3072, 1024), (128, 64, 128), (6000, 1024, 2048),
+                                   (5003, 1288, 320)])
 def test_gemm_bf16_out_with_bf16_residual_tma_path(cuda_dev, M, N, K):
     """bf16 output + bf16 residual: both move through TMA (staging tile); includes the in-place x = x + f(x) form."""
     from fdm_b200 import lib
