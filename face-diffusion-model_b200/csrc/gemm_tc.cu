@@ -23,6 +23,7 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int ACC_STAGES = 2;
+constexpr int NB_STAGE = 4;  // epilogue staging tiles per warp
 
 // CG = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
 // CG = 2: a CTA pair (cluster of 2 SMs) per 256 x BLOCK_N tile (cta_group::2): each CTA stages its own 128 rows of A and
@@ -34,10 +35,10 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N / CG) == 256 ? 4 : ((BLOCK_N / CG) == 128 ? 6 : 8);
+  static constexpr int STAGES = (BLOCK_N / CG) == 256 ? 3 : ((BLOCK_N / CG) == 128 ? 5 : 6);
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int BAR_BYTES = 1024;                  // barriers + TMEM slot, keeps the staging tiles 1024-aligned
-  static constexpr int STAGING_BYTES = 4 * 2 * 4096;      // 4 epilogue warps x 2 tiles x (32 rows x 128 B)
+  static constexpr int STAGING_BYTES = 4 * NB_STAGE * 4096;  // 4 epilogue warps x NB_STAGE tiles x (32 rows x 128 B)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024: manual alignment
 };
 
@@ -320,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + ACC_STAGES + a); };
-  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 2 * ACC_STAGES + 1 + 2 * w + b); };
+  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 2 * ACC_STAGES + 1 + NB_STAGE * w + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5;
@@ -345,8 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(tempty_bar(a), 128 * CG);  // epilogue threads of both CTAs arrive on the leader's barrier
     }
     for (int w = 0; w < 4; ++w) {
-      mbar_init(res_bar(w, 0), 1);
-      mbar_init(res_bar(w, 1), 1);
+      for (int b = 0; b < NB_STAGE; ++b) mbar_init(res_bar(w, b), 1);
     }
     fence_barrier_init();
   } else if (warp == 2) {
@@ -424,41 +424,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> swizzled smem staging -> TMA store =====
+    // Each warp owns NB_STAGE staging tiles (32 rows x 128 B) used round-robin over a running chunk counter g, so the
+    // TMA store of chunk g (read latency ~2-3k cycles) has NB_STAGE - 1 chunks of math to finish before its tile is
+    // reused; with two tiles the epilogue, not the MMA, set the pace (11-16k cycles per 128 x 256 tile vs 8k of MMA).
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
-    const uint32_t stage_base = bar_base + C::BAR_BYTES + static_cast<uint32_t>(warp - 2) * 8192u;
+    const int ew = warp - 2;
+    const uint32_t stage_base = bar_base + C::BAR_BYTES + static_cast<uint32_t>(ew) * (NB_STAGE * 4096u);
     const bool out_bf16 = ep.out_dtype == FDM_BF16;
     const int CW = out_bf16 ? 64 : 32;  // output columns per 128-byte staging row
-    int acc = 0, buf = 0;
+    int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t g = 0;  // chunks processed by this warp so far
     if (ep.tma_r) {
-      // ---- bf16 out + bf16 residual, both through TMA: the residual chunk is fetched into the staging tile one chunk
+      // ---- bf16 out + bf16 residual, both through TMA: the residual chunk is fetched into the staging tile two chunks
       //      ahead, each thread adds its own row in place, and the same tile is handed to the TMA store engine ----
-      const int ew = warp - 2;
-      uint32_t rphase = 0u;  // bit b = parity of residual barrier b
+      auto n_chunks_of = [&](int tile) {
+        const int n_blk = tile % n_tiles;
+        return min(BLOCK_N / 64, (N - n_blk * BLOCK_N + 63) / 64);
+      };
+      auto issue_residual = [&](int tile, int c, uint32_t gg) {  // lane 0 only
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const uint32_t b = gg % NB_STAGE;
+        bulk_wait_read<1>();  // the store that last used this staging tile (NB_STAGE chunks ago) has released it
+        mbar_expect_tx(res_bar(ew, b), 4096);
+        tma_load_2d(stage_base + b * 4096u, &tmap_r, res_bar(ew, b), n_blk * BLOCK_N + c * 64,
+                    m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32);
+      };
+      // look-ahead cursor: position of chunk g + 2
+      int la_tile = tile_first, la_c = 0;
+      uint32_t la_g = 0;
+      auto advance_la = [&]() {
+        ++la_g;
+        if (++la_c >= n_chunks_of(la_tile)) { la_c = 0; la_tile += tile_step; }
+      };
+      if (lane == 0) {
+        for (int i = 0; i < 2 && la_tile < num_tiles; ++i) { issue_residual(la_tile, la_c, la_g); advance_la(); }
+      }
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         const int row_w = m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32;
         const int n_base = n_blk * BLOCK_N;
         const int n_chunks = min(BLOCK_N / 64, (N - n_base + 63) / 64);
-        if (lane == 0) {
-          bulk_wait_read<1>();  // the store issued two chunks ago (same staging tile) has finished reading it
-          mbar_expect_tx(res_bar(ew, buf), 4096);
-          tma_load_2d(stage_base + buf * 4096u, &tmap_r, res_bar(ew, buf), n_base, row_w);
-        }
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = 0; c < n_chunks; ++c, ++g) {
           const int col0 = n_base + c * 64;
-          const uint32_t sbuf = stage_base + buf * 4096u;
-          if (c + 1 < n_chunks && lane == 0) {
-            bulk_wait_read<0>();  // previous chunk's store has released the other staging tile
-            mbar_expect_tx(res_bar(ew, buf ^ 1), 4096);
-            tma_load_2d(stage_base + (buf ^ 1) * 4096u, &tmap_r, res_bar(ew, buf ^ 1), col0 + 64, row_w);
-          }
-          mbar_wait(res_bar(ew, buf), (rphase >> buf) & 1u);
-          rphase ^= 1u << buf;
+          const uint32_t b = g % NB_STAGE;
+          const uint32_t sbuf = stage_base + b * 4096u;
+          if (lane == 0 && la_tile < num_tiles) { issue_residual(la_tile, la_c, la_g); advance_la(); }
+          mbar_wait(res_bar(ew, b), (g / NB_STAGE) & 1u);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             if (col0 + half * 32 >= N) break;  // warp-uniform
@@ -494,7 +510,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_store_2d(&tmap_c, sbuf, col0, row_w);
             bulk_commit();
           }
-          buf ^= 1;
         }
         tcgen05_fence_before();
         if (CG == 2) mbar_arrive_remote(tempty_bar(acc), 0);
@@ -511,11 +526,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CW, ++g) {
         const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= N) break;  // warp-uniform
-        const uint32_t sbuf = stage_base + buf * 4096u;
-        if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this tile
+        const uint32_t sbuf = stage_base + (g % NB_STAGE) * 4096u;
+        if (lane == 0) bulk_wait_read<NB_STAGE - 1>();  // the store issued NB_STAGE chunks ago has finished reading this tile
         __syncwarp();
         {
           uint32_t r[32];
@@ -581,7 +596,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           __syncwarp();
         }
-        buf ^= 1;
       }
       tcgen05_fence_before();
       if (CG == 2) mbar_arrive_remote(tempty_bar(acc), 0);
