@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU")
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--ddpm-steps", type=int, default=1000)
-    ap.add_argument("--preset", default="vocaset", choices=["vocaset", "mead"])
+    ap.add_argument("--preset", default="vocaset", choices=["vocaset", "mead", "biwi"])
     ap.add_argument("--no-cfg", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -65,12 +65,18 @@ def build_models(preset, device, precision):
         from models.utils.config import vocaset_vq_vae_args as vargs
         from video_diffusion_pytorch.diffusion_BIWI_encoder_decoder import GaussianDiffusion
         fdm = FDM(feature_dim=1024)
-    else:
+    elif preset == "mead":
         from models.fdm_vqvae_mead import FDM
         from models.vq_vae_emotion import VQAutoEncoder
         from utiles.args import vq_vae_args as vargs
         from video_diffusion_pytorch.diffusion_mead_encoder_decoder import GaussianDiffusion
         fdm = FDM(feature_dim=512, vertice_dim=5023 * 3, struct="Dec")
+    else:
+        from models.fdm import FDM
+        from models.vq_vae import VQAutoEncoder
+        from models.utils.config import biwi_vq_vae_args as vargs
+        from video_diffusion_pytorch.diffusion_BIWI_encoder_decoder import GaussianDiffusion
+        fdm = FDM(feature_dim=1024, struct="Dec")
     torch.nn.init.normal_(fdm.latent_decoder.weight, std=0.02)  # reference zero-init would make x0_hat == 0
     ae = VQAutoEncoder(vargs())
     torch.nn.init.normal_(ae.quantize.embedding.weight)
@@ -206,8 +212,9 @@ def cpu_reference_sample(args, n_ddpm_steps):
     fdm, ae, diff = build_models(args.preset, None, "fp32")
     P = R.PRESETS[args.preset]
     sd = {k: v.detach() for k, v in fdm.state_dict().items()}
-    from transformers import HubertModel
-    hf = HubertModel(R.audio_encoder_config("hubert", False)).eval()
+    from transformers import HubertModel, Wav2Vec2Model
+    kind = P["audio"]
+    hf = (HubertModel if kind == "hubert" else Wav2Vec2Model)(R.audio_encoder_config(kind, False)).eval()
     hf.load_state_dict({k[len("audio_encoder."):]: v for k, v in sd.items() if k.startswith("audio_encoder.")})
     n_samples = int(16000 * args.seconds)
     audio = synthetic_audio(1, n_samples, 0)[0]

@@ -17,12 +17,14 @@ bq = torch.zeros(3 * d, device=dev); b1 = torch.zeros(d, device=dev)
 qkv = torch.empty(M, 3 * d, device=dev, dtype=torch.bfloat16)
 out = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
 gam = torch.ones(d, device=dev); bet = torch.zeros(d, device=dev)
+ttab = torch.randn(1000, d, device=dev); tidx = torch.tensor([5], dtype=torch.int32, device=dev)
 slopes = torch.tensor([2.0 ** -(i + 1) for i in range(H)], device=dev)
 kern = {
     "gemm_qkv(25344x3072x1024)": (lambda: lib.gemm(x, wq, qkv, bias=bq), 2.0 * M * 3 * d * d),
     "gemm_ffn2(25344x1024x2048,+res)": (lambda: lib.gemm(h2, w2, out, bias=b1, residual=x), 2.0 * M * d * 2 * d),
     "attention(128 seq x 8 heads x 198)": (lambda: lib.self_attention(qkv[:, 0:], qkv[:, d:], qkv[:, 2 * d:], out, S, T, T, H, 128, 0.0884, slopes=slopes, period=30), 4.0 * S * H * T * T * 128),
     "layernorm(25344x1024)": (lambda: lib.layernorm(out, out, g1=gam, b1=bet), 0.0),
+    "layernorm_double(25344x1024,+cross,+time)": (lambda: lib.layernorm(x, out, g1=gam, b1=bet, r2=x[:M // 2], vec2=ttab, vec_index_dev=tidx, g2=gam, b2=bet), 0.0),
 }
 Q = "clocks.sm,power.draw"
 res = {}
