@@ -7,10 +7,10 @@
 // Implicit 1-D convolutions (VQ-decoder Conv1d k5, HuBERT conv stack / positional conv) are the same
 // kernel: the producer shifts the TMA row coordinate per filter tap instead of materialising im2col.
 //
-// CTA layout (192 threads, 1 CTA/SM, persistent over a static tile schedule):
+// CTA layout (320 threads, 1 CTA/SM, persistent over a static tile schedule):
 //   warp 0      TMA producer   (one elected lane)         smem ring: STAGES x {A 128x64, W BLOCK_Nx64}
 //   warp 1      MMA issuer     (one elected lane)         tcgen05.mma 128 x BLOCK_N x 16, cta_group::1
-//   warps 2-5   epilogue       (TMEM lane quadrant = warp & 3), double-buffered TMEM accumulator
+//   warps 2-9   epilogue       (TMEM lane quadrant = warp & 3, column half = (warp-2)/4), double-buffered TMEM accumulator
 // Pipelines: full/empty mbarriers (TMA <-> MMA), tmem_full/tmem_empty mbarriers (MMA <-> epilogue).
 #include "common.cuh"
 #include <cuda.h>
@@ -21,9 +21,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int EPI_WARPS = 8;
 constexpr int ACC_STAGES = 2;
-constexpr int NB_STAGE = 4;  // epilogue staging tiles per warp
+constexpr int NB_STAGE = 2;  // epilogue staging tiles per warp
 
 // CG = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
 // CG = 2: a CTA pair (cluster of 2 SMs) per 256 x BLOCK_N tile (cta_group::2): each CTA stages its own 128 rows of A and
@@ -35,10 +36,11 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // ring depth: ~64 B/clk/SM of operand traffic x ~2.5k cycles of TMA latency wants ~160 KB in flight
   static constexpr int STAGES = (BLOCK_N / CG) == 256 ? 3 : ((BLOCK_N / CG) == 128 ? 5 : 6);
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int BAR_BYTES = 1024;                  // barriers + TMEM slot, keeps the staging tiles 1024-aligned
-  static constexpr int STAGING_BYTES = 4 * NB_STAGE * 4096;  // 4 epilogue warps x NB_STAGE tiles x (32 rows x 128 B)
+  static constexpr int STAGING_BYTES = EPI_WARPS * NB_STAGE * 4096;  // per warp: NB_STAGE tiles of 32 rows x 128 B
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024: manual alignment
 };
 
@@ -343,9 +345,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128 * CG);  // epilogue threads of both CTAs arrive on the leader's barrier
+      mbar_init(tempty_bar(a), EPI_WARPS * 32 * CG);  // epilogue threads of both CTAs arrive on the leader's barrier
     }
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < EPI_WARPS; ++w) {
       for (int b = 0; b < NB_STAGE; ++b) mbar_init(res_bar(w, b), 1);
     }
     fence_barrier_init();
@@ -427,8 +429,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // Each warp owns NB_STAGE staging tiles (32 rows x 128 B) used round-robin over a running chunk counter g, so the
     // TMA store of chunk g (read latency ~2-3k cycles) has NB_STAGE - 1 chunks of math to finish before its tile is
     // reused; with two tiles the epilogue, not the MMA, set the pace (11-16k cycles per 128 x 256 tile vs 8k of MMA).
+    // Eight warps: warps w and w+4 share a TMEM lane quadrant (rows) and split the tile's columns in two halves.
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
     const int ew = warp - 2;
+    const int col_half = ew >> 2;
+    const int c_begin = BLOCK_N >= 128 ? col_half * (BLOCK_N / 2) : 0;                       // this warp's columns of the tile
+    const int c_end = BLOCK_N >= 128 ? c_begin + BLOCK_N / 2 : (col_half == 0 ? BLOCK_N : 0);
     const uint32_t stage_base = bar_base + C::BAR_BYTES + static_cast<uint32_t>(ew) * (NB_STAGE * 4096u);
     const bool out_bf16 = ep.out_dtype == FDM_BF16;
     const int CW = out_bf16 ? 64 : 32;  // output columns per 128-byte staging row
@@ -438,42 +444,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ep.tma_r) {
       // ---- bf16 out + bf16 residual, both through TMA: the residual chunk is fetched into the staging tile two chunks
       //      ahead, each thread adds its own row in place, and the same tile is handed to the TMA store engine ----
-      auto n_chunks_of = [&](int tile) {
+      auto n_chunks_of = [&](int tile) {  // 64-column chunks of this warp's half that start inside the matrix
         const int n_blk = tile % n_tiles;
-        return min(BLOCK_N / 64, (N - n_blk * BLOCK_N + 63) / 64);
+        const int avail = N - n_blk * BLOCK_N - c_begin;
+        return avail <= 0 ? 0 : min((c_end - c_begin) / 64, (avail + 63) / 64);
       };
       auto issue_residual = [&](int tile, int c, uint32_t gg) {  // lane 0 only
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         const uint32_t b = gg % NB_STAGE;
-        bulk_wait_read<1>();  // the store that last used this staging tile (NB_STAGE chunks ago) has released it
+        bulk_wait_read<0>();  // the store that last used this staging tile (issued one chunk ago) has released it
         mbar_expect_tx(res_bar(ew, b), 4096);
-        tma_load_2d(stage_base + b * 4096u, &tmap_r, res_bar(ew, b), n_blk * BLOCK_N + c * 64,
+        tma_load_2d(stage_base + b * 4096u, &tmap_r, res_bar(ew, b), n_blk * BLOCK_N + c_begin + c * 64,
                     m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32);
       };
       // look-ahead cursor: position of chunk g + 2
       int la_tile = tile_first, la_c = 0;
       uint32_t la_g = 0;
+      auto skip_empty = [&]() {  // tiles whose columns of this half lie outside the matrix have no chunks
+        while (la_tile < num_tiles && n_chunks_of(la_tile) == 0) la_tile += tile_step;
+      };
       auto advance_la = [&]() {
         ++la_g;
-        if (++la_c >= n_chunks_of(la_tile)) { la_c = 0; la_tile += tile_step; }
+        if (++la_c >= n_chunks_of(la_tile)) { la_c = 0; la_tile += tile_step; skip_empty(); }
       };
       if (lane == 0) {
-        for (int i = 0; i < 2 && la_tile < num_tiles; ++i) { issue_residual(la_tile, la_c, la_g); advance_la(); }
+        skip_empty();
+        if (la_tile < num_tiles) { issue_residual(la_tile, la_c, la_g); advance_la(); }  // one chunk ahead
       }
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         const int row_w = m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32;
-        const int n_base = n_blk * BLOCK_N;
-        const int n_chunks = min(BLOCK_N / 64, (N - n_base + 63) / 64);
+        const int n_base = n_blk * BLOCK_N + c_begin;
+        const int n_chunks = n_chunks_of(tile);
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
-        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c_begin;
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c, ++g) {
           const int col0 = n_base + c * 64;
           const uint32_t b = g % NB_STAGE;
           const uint32_t sbuf = stage_base + b * 4096u;
-          if (lane == 0 && la_tile < num_tiles) { issue_residual(la_tile, la_c, la_g); advance_la(); }
           mbar_wait(res_bar(ew, b), (g / NB_STAGE) & 1u);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -507,6 +517,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
+            // next chunk's residual into the other staging tile: its last store was issued a whole chunk ago
+            if (la_tile < num_tiles) { issue_residual(la_tile, la_c, la_g); advance_la(); }
             tma_store_2d(&tmap_c, sbuf, col0, row_w);
             bulk_commit();
           }
@@ -526,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CW, ++g) {
+      for (int c0 = c_begin; c0 < c_end; c0 += CW, ++g) {
         const int col0 = n_blk * BLOCK_N + c0;
         if (col0 >= N) break;  // warp-uniform
         const uint32_t sbuf = stage_base + (g % NB_STAGE) * 4096u;
@@ -681,7 +693,8 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   const int num_k_blocks = static_cast<int>(ceil_div64(a.K, BLOCK_K));
   const int kb_per_tap = taps > 1 ? static_cast<int>(a.tap_k / BLOCK_K) : num_k_blocks;
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
-  const int64_t slots = fdm_sm_count() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
+  static const int sm_limit = [] { const char* e = getenv("FDM_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();  // experiments only
+  const int64_t slots = (sm_limit > 0 ? sm_limit : fdm_sm_count()) / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
   const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
   FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
                                 tm_c, tm_r, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
@@ -730,7 +743,6 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   static const bool two_cta = [] { const char* e = getenv("FDM_B200_GEMM_2CTA"); return !(e && e[0] == '0'); }();
   if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2)
     return launch<256, 2>(a, ep, s);
-  if (a.N >= 256 && m_tiles * ceil_div64(a.N, 256) >= sms) return launch<256>(a, ep, s);
   if (a.N >= 128 && m_tiles * ceil_div64(a.N, 128) >= sms) return launch<128>(a, ep, s);
   if (a.N > 64 && a.N % 64 != 0 && a.N >= 128) return launch<128>(a, ep, s);
   return launch<64>(a, ep, s);
