@@ -58,10 +58,10 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
 
 // Cooperative 64-row tile load. Thread -> (row r_base + ROWS_PER_IT * it, chunk c): the swizzled chunk and the
 // per-iteration strides are loop-invariant, so a tile costs one compare + one cp.async per 16 bytes.
-template <int DH>
+template <int DH, int NTHR = THREADS>
 struct TileLoader {
   static constexpr int CH = DH / 8;                 // 16-byte chunks per row
-  static constexpr int ROWS_PER_IT = THREADS / CH;  // 8 (DH = 128) or 16 (DH = 64)
+  static constexpr int ROWS_PER_IT = NTHR / CH;     // 8 (DH = 128) or 16 (DH = 64); 8 for DH = 256 with 256 threads
   static constexpr int ITERS = 64 / ROWS_PER_IT;
   int r_base;
   uint32_t soff;   // smem byte offset of (r_base, c) with the swizzle applied
@@ -292,6 +292,211 @@ __global__ void __launch_bounds__(THREADS, 3) attn_mma_kernel(const fdm_attn_arg
   }
 }
 
+// ---- head dim 256 (BIWI FDM: 4 heads x 256) ------------------------------------------------------------------
+// Same algorithm with 8 warps per CTA: warps w and w+4 own the same 16 query rows, both compute the full 16 x 64
+// score tile (Q.K^T over 256 dims, Q fragments re-read from smem per key block instead of pinned in registers) and
+// each accumulates one 128-column half of O, so the per-thread accumulator stays at 64 registers.
+template <bool CAUSAL>
+__global__ void __launch_bounds__(256, 1) attn_mma256_kernel(const fdm_attn_args a) {
+  constexpr int DH = 256, KS = DH / 16, NTV = 16;  // NTV: n-tiles of this warp's 128-column half of V
+  constexpr int TILE = 64 * DH * 2;                // 32 KB
+  extern __shared__ __align__(128) uint8_t smem[];
+  // slots: [Q][K0][V0][K1][V1]
+  const uint32_t sQ = smem_u32(smem), s0 = sQ + TILE;
+  float* tab = reinterpret_cast<float*>(smem + 5 * TILE);
+
+  const int T = static_cast<int>(a.T);
+  const int q0 = blockIdx.x * QB, h = blockIdx.y;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.z) * a.t_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = warp & 3, vhalf = warp >> 2;  // query-row group, V column half
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float scale2 = a.scale * LOG2E;
+
+  const __nv_bfloat16* Qg = reinterpret_cast<const __nv_bfloat16*>(a.Q) + row0 * a.ldq + static_cast<int64_t>(h) * DH;
+  const __nv_bfloat16* Kg = reinterpret_cast<const __nv_bfloat16*>(a.K) + row0 * a.ldk + static_cast<int64_t>(h) * DH;
+  const __nv_bfloat16* Vg = reinterpret_cast<const __nv_bfloat16*>(a.V) + row0 * a.ldv + static_cast<int64_t>(h) * DH;
+
+  const int k_end = CAUSAL ? min(T, q0 + QB) : T;
+  const int n_kb = (k_end + KB - 1) / KB;
+  const int tabn = T + 64;
+
+  const TileLoader<DH, 256> tl;
+  pdl_trigger();
+  pdl_wait();
+  tl.load(sQ, Qg, a.ldq, q0, T);
+  tl.load(s0, Kg, a.ldk, 0, T);
+  tl.load(s0 + TILE, Vg, a.ldv, 0, T);
+  cp_async_commit();
+  if (n_kb > 1) {
+    tl.load(s0 + 2 * TILE, Kg, a.ldk, KB, T);
+    tl.load(s0 + 3 * TILE, Vg, a.ldv, KB, T);
+  }
+  cp_async_commit();
+  if (CAUSAL) {
+    const float slope2 = a.slopes[h] * LOG2E;
+    const int period = a.period;
+    for (int k = threadIdx.x; k < tabn; k += 256) {
+      const int delta = (T - 1) - k;
+      const float v = delta < 0 ? -INFINITY : -slope2 * static_cast<float>(delta / period);
+      tab[k] = v;
+      tab[TAB_MAX + k + 1] = v;
+    }
+  }
+  cp_async_wait<1>();
+  __syncthreads();
+
+  float o[NTV][4];
+#pragma unroll
+  for (int i = 0; i < NTV; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int t_row0 = q0 + wq * 16 + g;
+  const float* tabp[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int kb0 = (T - 1) - (t_row0 + 8 * r) + 2 * tq;
+    tabp[r] = (kb0 & 1) ? tab + TAB_MAX + kb0 + 1 : tab + kb0;
+  }
+  const int warp_last_row = q0 + wq * 16 + 15;
+
+  for (int kb = 0; kb < n_kb; ++kb) {
+    const uint32_t kbuf = s0 + (kb & 1) * 2 * TILE, vbuf = kbuf + TILE;
+    const int j0 = kb * KB;
+    if (!CAUSAL || j0 <= warp_last_row) {
+      float s[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll 4
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t qf[4];
+        ldsm_x4(sQ + tile_off<DH>(wq * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[0], qf[1], qf[2], qf[3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b0, b1, b2, b3;
+          const int key = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+          const int c = ks * 2 + ((lane >> 3) & 1);
+          ldsm_x4(kbuf + tile_off<DH>(key, c), b0, b1, b2, b3);
+          mma_bf16(s[2 * np], qf, b0, b1);
+          mma_bf16(s[2 * np + 1], qf, b2, b3);
+        }
+      }
+      if (CAUSAL) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const float2 b0 = *reinterpret_cast<const float2*>(tabp[0] + j0 + 8 * n);
+          const float2 b1 = *reinterpret_cast<const float2*>(tabp[1] + j0 + 8 * n);
+          s[n][0] = fmaf(s[n][0], scale2, b0.x);
+          s[n][1] = fmaf(s[n][1], scale2, b0.y);
+          s[n][2] = fmaf(s[n][2], scale2, b1.x);
+          s[n][3] = fmaf(s[n][3], scale2, b1.y);
+        }
+      } else {
+        const bool edge = j0 + KB > T;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = s[n][e] * scale2;
+            s[n][e] = (edge && j0 + n * 8 + tq * 2 + (e & 1) >= T) ? -INFINITY : x;
+          }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);
+      const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;
+      const float corr0 = fast_exp2(m_run[0] - ms0), corr1 = fast_exp2(m_run[1] - ms1);
+      m_run[0] = mn0;
+      m_run[1] = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const float p0 = fast_exp2(s[n][0] - ms0), p1 = fast_exp2(s[n][1] - ms0);
+        const float p2 = fast_exp2(s[n][2] - ms1), p3 = fast_exp2(s[n][3] - ms1);
+        rs0 += p0 + p1;
+        rs1 += p2 + p3;
+        pf[n >> 1][(n & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pf[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+      rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+      rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+      rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+      rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+      l_run[0] = l_run[0] * corr0 + rs0;
+      l_run[1] = l_run[1] * corr1 + rs1;
+#pragma unroll
+      for (int i = 0; i < NTV; ++i) {
+        o[i][0] *= corr0; o[i][1] *= corr0;
+        o[i][2] *= corr1; o[i][3] *= corr1;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int np = 0; np < NTV / 2; ++np) {
+          uint32_t b0, b1, b2, b3;
+          const int key = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+          const int c = vhalf * 16 + np * 2 + (lane >> 4);
+          ldsm_x4_t(vbuf + tile_off<DH>(key, c), b0, b1, b2, b3);
+          mma_bf16(o[2 * np], pf[ks], b0, b1);
+          mma_bf16(o[2 * np + 1], pf[ks], b2, b3);
+        }
+      }
+    }
+    __syncthreads();
+    if (kb + 2 < n_kb) {
+      tl.load(kbuf, Kg, a.ldk, (kb + 2) * KB, T);
+      tl.load(vbuf, Vg, a.ldv, (kb + 2) * KB, T);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+  }
+
+  // normalise and stage through the Q tile (no longer needed), then coalesced 16-byte stores
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+#pragma unroll
+  for (int i = 0; i < NTV; ++i) {
+    const int r0 = wq * 16 + g, r1 = r0 + 8;
+    const uint32_t w0 = sQ + tile_off<DH>(r0, vhalf * 16 + i) + tq * 4;
+    const uint32_t w1 = sQ + tile_off<DH>(r1, vhalf * 16 + i) + tq * 4;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(w0), "r"(pack_bf16(o[i][0] * inv0, o[i][1] * inv0)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(w1), "r"(pack_bf16(o[i][2] * inv1, o[i][3] * inv1)) : "memory");
+  }
+  __syncthreads();
+  __nv_bfloat16* Og = reinterpret_cast<__nv_bfloat16*>(a.O) + row0 * a.ldo + static_cast<int64_t>(h) * DH;
+  constexpr int CH = DH / 8;
+  for (int i = threadIdx.x; i < QB * CH; i += 256) {
+    const int r = i / CH, c = i - r * CH;
+    if (q0 + r < T) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sQ + tile_off<DH>(r, c)));
+      *reinterpret_cast<uint4*>(Og + static_cast<int64_t>(q0 + r) * a.ldo + c * 8) = v;
+    }
+  }
+}
+
+template <bool CAUSAL>
+int launch256(const fdm_attn_args& a, cudaStream_t stream) {
+  const size_t smem = 5 * 64 * 256 * 2 + 2 * TAB_MAX * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    FDM_CHECK_CUDA(cudaFuncSetAttribute(attn_mma256_kernel<CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = true;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div64(a.T, QB)), static_cast<unsigned>(a.H), static_cast<unsigned>(a.B));
+  FDM_CHECK_CUDA(fdm_launch_pdl(attn_mma256_kernel<CAUSAL>, grid, dim3(256), smem, stream, 1, a));
+  return 0;
+}
+
 template <int DH, bool CAUSAL>
 int launch(const fdm_attn_args& a, cudaStream_t stream) {
   const size_t smem = 4 * 64 * DH * 2 + 2 * TAB_MAX * sizeof(float);
@@ -309,12 +514,13 @@ int launch(const fdm_attn_args& a, cudaStream_t stream) {
 
 int fdm_attention_mma_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled) {
   *handled = false;
-  if (a.dtype != FDM_BF16 || (a.dh != 64 && a.dh != 128)) return 0;
+  if (a.dtype != FDM_BF16 || (a.dh != 64 && a.dh != 128 && a.dh != 256)) return 0;
   // 16-byte cp.async / vector stores need aligned rows; the bias table covers T <= 1024
   const uintptr_t al = reinterpret_cast<uintptr_t>(a.Q) | reinterpret_cast<uintptr_t>(a.K) | reinterpret_cast<uintptr_t>(a.V) |
                        reinterpret_cast<uintptr_t>(a.O);
   if ((al & 15u) != 0 || a.ldq % 8 || a.ldk % 8 || a.ldv % 8 || a.ldo % 8 || a.T > 1024) return 0;
   *handled = true;
+  if (a.dh == 256) return a.bias_mode == 1 ? launch256<true>(a, stream) : launch256<false>(a, stream);
   if (a.bias_mode == 1) return a.dh == 64 ? launch<64, true>(a, stream) : launch<128, true>(a, stream);
   return a.dh == 64 ? launch<64, false>(a, stream) : launch<128, false>(a, stream);
 }
