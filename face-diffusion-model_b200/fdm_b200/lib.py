@@ -68,6 +68,7 @@ EXPORTS = {
     "fdm_advance_cursor": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "fdm_philox_normal": (C.c_int, [_vp, _i64, _i64, _u64, _i64, _i32, _vp]),
     "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "fdm_vq_quantize_ex": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "fdm_transpose_bcl_to_blc": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp]),
     "fdm_pad_time": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
@@ -290,9 +291,16 @@ def philox_normal(out: torch.Tensor, seed: int, clip_index0: int, t: int) -> tor
     return out
 
 
+VQ_AUTO, VQ_FFMA, VQ_TENSOR = 0, 1, 2
+
+
 def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, n_codes: int, code_offset=None, want_bdl=True,
-                want_rows=False):
-    """z (B, L, D) f32 -> (indices (B*L, 1) int64, z_q (B, D, L) or None, z_q rows (B, L, D) or None)."""
+                want_rows=False, algo: int = VQ_AUTO, recheck_rows: Optional[torch.Tensor] = None,
+                dbg_acc: Optional[torch.Tensor] = None):
+    """z (B, L, D) f32 -> (indices (B*L, 1) int64, z_q (B, D, L) or None, z_q rows (B, L, D) or None).
+    algo: VQ_AUTO (tensor-core filter + exact recheck when D = 64), VQ_FFMA, VQ_TENSOR; identical indices either way.
+    recheck_rows: optional zeroed int64[1] device counter of rows that took the exact pass (tensor path);
+    dbg_acc: optional (B*L, n_codes) f32 dump of the tensor-core dot products (tests)."""
     lib = require_device()
     assert z.dtype == torch.float32 and z.is_contiguous() and codebook.dtype == torch.float32 and codebook.is_contiguous()
     B, L, D = z.shape
@@ -301,8 +309,12 @@ def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, n_codes: int, code_offs
     zr = torch.empty((B, L, D), dtype=torch.float32, device=z.device) if want_rows else None
     if code_offset is not None:
         assert code_offset.dtype == torch.int64 and code_offset.numel() == B
-    _check(lib.fdm_vq_quantize(_ptr(z), _ptr(codebook), _ptr(code_offset), B, L, D, n_codes, _ptr(idx), _ptr(zq),
-                               _ptr(zr), _stream()))
+    if recheck_rows is not None:
+        assert recheck_rows.dtype == torch.int64 and recheck_rows.numel() == 1
+    if dbg_acc is not None:
+        assert dbg_acc.dtype == torch.float32 and dbg_acc.is_contiguous() and dbg_acc.numel() == B * L * n_codes
+    _check(lib.fdm_vq_quantize_ex(_ptr(z), _ptr(codebook), _ptr(code_offset), B, L, D, n_codes, _ptr(idx), _ptr(zq),
+                                  _ptr(zr), algo, _ptr(recheck_rows), _ptr(dbg_acc), _stream()))
     _launched()
     return idx, zq, zr
 

@@ -262,6 +262,86 @@ def test_vq_quantize(cuda_dev, D, L):
     assert idx.min() >= 0 and idx.max() < n
 
 
+def _vq_case(name, gen):
+    """Synthetic (z (B, L, 64), codebook (n_slices*n, 64), n, offsets) cases for the tensor-core VQ path."""
+    D = 64
+    if name == "normal_mead":  # per-clip emotion slices, ragged last tile
+        B, L, n = 5, 792, 256
+        return torch.randn(B, L, D, generator=gen), torch.randn(7 * n, D, generator=gen), n, [0, 768, 1536, 1536, 256]
+    if name == "reference_init":  # uniform(+-1/n) codes against unit-variance latents: all distances nearly equal
+        B, L, n = 2, 3168, 256
+        return torch.randn(B, L, D, generator=gen), (torch.rand(n, D, generator=gen) * 2 - 1) / n, n, None
+    if name == "ragged":
+        return torch.randn(3, 129, D, generator=gen), torch.randn(128, D, generator=gen), 128, None
+    if name == "single_row":
+        return torch.randn(4, 1, D, generator=gen), torch.randn(64, D, generator=gen), 64, None
+    if name == "ties":  # duplicate and nearly-duplicate codes, latents on codes / midpoints / zero, wide dynamic range
+        B, L, n = 2, 1000, 256
+        cb = torch.randn(n, D, generator=gen)
+        cb[100] = cb[7]                       # exact duplicate: lowest index must win
+        cb[200] = cb[7]
+        cb[150] = cb[31] * (1 + 1e-7)         # one-ulp-ish neighbours
+        cb[151] = cb[31] + 1e-6 * torch.randn(D, generator=gen)
+        z = torch.randn(B, L, D, generator=gen)
+        pick = torch.randint(0, n, (B, L), generator=gen)
+        z[:, 0:200] = cb[pick[:, 0:200]]
+        other = torch.randint(0, n, (B, L), generator=gen)
+        z[:, 200:400] = 0.5 * (cb[pick[:, 200:400]] + cb[other[:, 200:400]])
+        z[:, 400:410] = 0.0
+        z[:, 410:500] = cb[7] + 1e-6 * torch.randn(B, 90, D, generator=gen)
+        z[1] *= 1e3
+        z[1, 700:] *= 1e-9
+        return z, cb, n, None
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("case", ["normal_mead", "reference_init", "ragged", "single_row", "ties"])
+def test_vq_tensor_path_bit_exact(cuda_dev, case):
+    """The tcgen05 filter + exact recheck must return the oracle's indices on every row (not just away from ties)."""
+    from fdm_b200 import lib
+    from oracle import reference_ops as R  # checker
+    gen = torch.Generator(device="cpu").manual_seed(sum(map(ord, case)))
+    z, cb, n, offs = _vq_case(case, gen)
+    B, L, D = z.shape
+    off = torch.tensor(offs, device=cuda_dev) if offs is not None else None
+    cnt = torch.zeros(1, dtype=torch.int64, device=cuda_dev)
+    idx, zq, zr = lib.vq_quantize(z.to(cuda_dev), cb.to(cuda_dev), n, code_offset=off, want_rows=True, algo=lib.VQ_TENSOR,
+                                  recheck_rows=cnt)
+    idx_f, _, _ = lib.vq_quantize(z.to(cuda_dev), cb.to(cuda_dev), n, code_offset=off, want_bdl=False, algo=lib.VQ_FFMA)
+    torch.cuda.synchronize()
+    idx, idx_f = idx.view(B, L).cpu(), idx_f.view(B, L).cpu()
+    for b in range(B):
+        o = offs[b] if offs is not None else 0
+        ref, _, _ = R.vq_quantize(z[b], cb[o:o + n])
+        assert torch.equal(idx[b], ref), (case, b, (idx[b] != ref).nonzero()[:5].tolist())
+        assert torch.equal(idx_f[b], ref)
+        assert torch.equal(zr[b].cpu(), cb[o + ref])
+        assert torch.equal(zq[b].cpu(), cb[o + ref].t())
+    frac = cnt.item() / (B * L)
+    if case in ("normal_mead", "ragged"):
+        assert frac < 0.02, frac       # random data: the exact pass is the rare path
+    if case == "ties":
+        assert cnt.item() >= 2 * 200   # the rows sitting on duplicated codes must have gone through it
+
+
+def test_vq_tensor_dot_error_bound(cuda_dev):
+    """Measures |acc - z.e| of the bf16x3 tensor-core dot products against fp64 and checks it sits well inside the
+    2^-12 |z||e| bound the kernel's candidate window assumes (vq_tc.cu header)."""
+    from fdm_b200 import lib
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    B, L, D, n = 2, 2048, 64, 256
+    z = torch.randn(B, L, D, generator=gen) * torch.logspace(-3, 3, L)[None, :, None]
+    cb = torch.randn(n, D, generator=gen) * torch.logspace(-2, 2, n)[:, None]
+    acc = torch.empty(B * L, n, device=cuda_dev)
+    lib.vq_quantize(z.to(cuda_dev), cb.to(cuda_dev), n, want_bdl=False, algo=lib.VQ_TENSOR, dbg_acc=acc)
+    torch.cuda.synchronize()
+    zd, ed = z.view(-1, D).double(), cb.double()
+    exact = zd @ ed.t()
+    scale = zd.norm(dim=1, keepdim=True) * ed.norm(dim=1)[None]
+    rel = ((acc.cpu().double() - exact).abs() / scale).max().item()
+    assert rel < 2.0 ** -14, rel
+
+
 def test_misc_kernels(cuda_dev):
     from fdm_b200 import lib
     import torch.nn.functional as F

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: EVQ-VAE quantise microbench — 1024 clips x 10 s (VOCASET preset: 8 159 232 latent rows
-x 64 dims against 256 codes). Reports kernel time, algorithmic HBM GB/s (4*D read + 8 B index + 4*D z_q per row)
-and checks a slice of rows bit-exactly against the CPU oracle."""
+x 64 dims against 256 codes). For each algorithm (FFMA = every chain on the fp32 pipes, TENSOR = tcgen05 filter + exact
+recheck) and output set (indices only / + z_q (B, D, L)) it reports kernel time (CUDA events), algorithmic HBM GB/s
+(4*D read + 8 B index [+ 4*D z_q] per row) against the measured HBM peak, the fraction of rows that needed the exact
+pass, and checks rows bit-exactly against the CPU oracle and the two algorithms against each other on all rows."""
 import json
 import os
 import sys
@@ -13,33 +15,49 @@ from fdm_b200 import lib  # noqa: E402
 
 lib.require_device()
 dev = torch.device("cuda:0")
-clips, T, fq, D, codes = 1024, 498, 16, 64, 256
+clips = int(os.environ.get("VQ_CLIPS", "1024"))
+T, fq, D, codes = 498, 16, 64, 256
 L = T * fq
 g = torch.Generator(device="cpu").manual_seed(0)
 cb = torch.randn(codes, D, generator=g).to(dev)
 z = torch.randn(clips, L, D, device=dev)
-for _ in range(3):
-    idx, zq, _ = lib.vq_quantize(z, cb, codes, want_bdl=True)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 5
-e0.record()
-for _ in range(reps):
-    idx, zq, _ = lib.vq_quantize(z, cb, codes, want_bdl=True)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
 rows = clips * L
-alg = rows * (4 * D + 8 + 4 * D)
-from oracle import reference_ops as R  # checker
-n_chk = 20000
-oi, ozq, _ = R.vq_quantize(z[0, :n_chk].cpu(), cb.cpu())
-ok = bool(torch.equal(oi, idx.view(clips, L)[0, :n_chk].cpu()))
 peak = 6556.8
 pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
 if os.path.exists(pk):
     peak = json.load(open(pk))["hbm_gbs"]
-print(json.dumps({"workload": "VQ quantise microbench, 1024 clips x 10 s (8159232 rows x 64, 256 codes)", "ms": ms,
-                  "rows_per_s": rows / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9, "hbm_peak_GBps": peak,
-                  "frac": alg / (ms / 1e3) / 1e9 / peak, "fp32_ffma_TFLOPs": 2.0 * rows * D * codes / (ms / 1e3) / 1e12,
-                  "bit_exact_vs_oracle_first_rows": ok, "rows_checked": n_chk}))
+from oracle import reference_ops as R  # checker
+n_chk = 20000
+oi, _, _ = R.vq_quantize(z[0, :n_chk].cpu(), cb.cpu())
+oi_last, _, _ = R.vq_quantize(z[-1, -n_chk:].cpu(), cb.cpu())
+out = {"workload": f"VQ quantise microbench, {clips} clips x 10 s ({rows} rows x 64, 256 codes)", "hbm_peak_GBps": peak, "runs": []}
+all_idx = {}
+for algo, name in ((lib.VQ_FFMA, "ffma"), (lib.VQ_TENSOR, "tensor")):
+    for want_zq in (False, True):
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            idx, zq, _ = lib.vq_quantize(z, cb, codes, want_bdl=want_zq, algo=algo)
+        torch.cuda.synchronize()
+        reps = 3 if algo == lib.VQ_FFMA else 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            idx, zq, _ = lib.vq_quantize(z, cb, codes, want_bdl=want_zq, algo=algo)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if algo == lib.VQ_TENSOR:
+            lib.vq_quantize(z, cb, codes, want_bdl=False, algo=algo, recheck_rows=cnt)
+            torch.cuda.synchronize()
+        alg = rows * (4 * D + 8 + (4 * D if want_zq else 0))
+        ok = bool(torch.equal(oi, idx.view(clips, L)[0, :n_chk].cpu()) and torch.equal(oi_last, idx.view(clips, L)[-1, -n_chk:].cpu()))
+        if want_zq:
+            ok = ok and bool(torch.equal(zq[0, :, :n_chk].cpu(), cb.cpu()[oi].t()))
+        all_idx[name] = idx
+        out["runs"].append({"algo": name, "z_q_written": want_zq, "ms": ms, "rows_per_s": rows / (ms / 1e3),
+                            "algorithmic_bytes": alg, "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
+                            "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / peak,
+                            "recheck_row_fraction": (cnt.item() / rows) if algo == lib.VQ_TENSOR else None,
+                            "bit_exact_vs_oracle": ok, "rows_checked_vs_oracle": 2 * n_chk})
+out["tensor_equals_ffma_all_rows"] = bool(torch.equal(all_idx["ffma"], all_idx["tensor"]))
+print(json.dumps(out))
