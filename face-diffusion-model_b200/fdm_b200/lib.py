@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdm_b200.so")
+LIB_PATH = os.environ.get("FDM_B200_LIB") or os.path.join(_HERE, "libfdm_b200.so")  # override: instrumented builds (tools/)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_MISH, ACT_GELU_ERF, ACT_GELU_TANH, ACT_LEAKY02 = range(6)
