@@ -91,6 +91,76 @@ __global__ void __launch_bounds__(256) hubert_conv0_kernel(const float* __restri
   }
 }
 
+// dst[r, 0:ld_dst] = cast(src[r, 0:cols]) followed by zeros: pads K to a 16-byte row pitch for the TMA-fed GEMMs
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, void* dst, int dd,
+                                                        int64_t ld_dst, int64_t rows, int64_t cols) {
+  const int64_t n = rows * ld_dst;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld_dst, c = i - r * ld_dst;
+    st_from_float(dst, dd, i, c < cols ? src[r * ld_src + c] : 0.f);
+  }
+}
+
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;  // every thread holds the total
+}
+
+// One CTA per clip: zero-mean / unit-variance normalisation of Wav2Vec2Processor (do_normalize=True:
+// (x - mean) / sqrt(var + 1e-7), population variance) followed by `Lout - L` zero samples (the demos append 1 s).
+__global__ void __launch_bounds__(1024) audio_normalize_pad_kernel(const float* __restrict__ in, int64_t L, float* __restrict__ out,
+                                                                   int64_t Lout, float eps) {
+  __shared__ float red[32];
+  const float* x = in + static_cast<int64_t>(blockIdx.x) * L;
+  float* y = out + static_cast<int64_t>(blockIdx.x) * Lout;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < L; i += blockDim.x) s += x[i];
+  const float mean = block_sum_1024(s, red) / static_cast<float>(L);
+  float q = 0.f;
+  for (int64_t i = threadIdx.x; i < L; i += blockDim.x) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+  const float var = block_sum_1024(q, red) / static_cast<float>(L);
+  const float rstd = 1.f / sqrtf(var + eps);
+  for (int64_t i = threadIdx.x; i < Lout; i += blockDim.x) y[i] = i < L ? (x[i] - mean) * rstd : 0.f;
+}
+
+// One CTA per frame: reduce over a vertex subset the squared L2 distance between prediction and ground truth
+// (metric/metric.py:115-138: per-frame max for LVE / FVE / all-vertex error, per-frame mean for EME).
+__global__ void __launch_bounds__(256) vertex_error_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int64_t V,
+                                                           const int64_t* __restrict__ idx, int64_t n, int mode,
+                                                           float* __restrict__ out) {
+  __shared__ float red[8];
+  const int64_t f = blockIdx.x;
+  const float* p = pred + f * V * 3;
+  const float* g = gt ? gt + f * V * 3 : nullptr;
+  const int64_t cnt = idx ? n : V;
+  float acc = mode == 0 ? 0.f : 0.f;  // distances are >= 0: 0 is the identity of both reductions
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t v = idx ? idx[i] : i;
+    float d2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float d = (g ? g[v * 3 + k] : 0.f) - p[v * 3 + k];
+      d2 += d * d;  // same order as np.sum(np.square(.), axis=2)
+    }
+    acc = mode == 0 ? fmaxf(acc, d2) : acc + d2;
+  }
+  acc = mode == 0 ? warp_max(acc) : warp_sum(acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < 8 ? red[lane] : 0.f;
+    t = mode == 0 ? warp_max(t) : warp_sum(t);
+    if (lane == 0) out[f] = mode == 0 ? t : t / static_cast<float>(cnt);
+  }
+}
+
 inline int grid1d(int64_t n) {
   const int64_t want = ceil_div64(n, 256), cap = static_cast<int64_t>(fdm_sm_count()) * 8;
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
@@ -137,6 +207,32 @@ extern "C" int fdm_hubert_conv0(const float* audio, int64_t B, int64_t L, const 
   else if (C == 32) hubert_conv0_kernel<1><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
   else if (C == 64) hubert_conv0_kernel<2><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
   else FDM_CHECK_ARG(false, "fdm_hubert_conv0: C=%lld not in {32,64,512}", (long long)C);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_cast_rows(const float* src, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst, int64_t rows,
+                             int64_t cols, void* stream) {
+  FDM_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= cols, "fdm_cast_rows: bad arguments");
+  cast_rows_kernel<<<grid1d(rows * ld_dst), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, dst, dst_dtype, ld_dst,
+                                                                                                rows, cols);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_audio_normalize_pad(const float* audio, int64_t B, int64_t L, float* out, int64_t Lout, float eps, void* stream) {
+  FDM_CHECK_ARG(audio && out && B > 0 && L > 0 && Lout >= L, "fdm_audio_normalize_pad: bad arguments");
+  audio_normalize_pad_kernel<<<static_cast<unsigned>(B), 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(audio, L, out, Lout, eps);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_vertex_error(const float* pred, const float* gt, int64_t frames, int64_t V, const int64_t* vertex_idx,
+                                int64_t n_idx, int32_t mode, float* out_per_frame, void* stream) {
+  FDM_CHECK_ARG(pred && out_per_frame && frames > 0 && V > 0 && (mode == 0 || mode == 1) && (!vertex_idx || n_idx > 0),
+                "fdm_vertex_error: bad arguments");
+  vertex_error_kernel<<<static_cast<unsigned>(frames), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, gt, V, vertex_idx, n_idx,
+                                                                                                        mode, out_per_frame);
   FDM_CHECK_LAUNCH();
   return 0;
 }

@@ -70,6 +70,9 @@ EXPORTS = {
     "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fdm_vq_quantize_ex": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
+    "fdm_cast_rows": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "fdm_audio_normalize_pad": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _f32, _vp]),
+    "fdm_vertex_error": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
     "fdm_transpose_bcl_to_blc": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp]),
     "fdm_pad_time": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
     "fdm_hubert_conv0": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp]),
@@ -317,6 +320,45 @@ def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, n_codes: int, code_offs
                                   _ptr(zr), algo, _ptr(recheck_rows), _ptr(dbg_acc), _stream()))
     _launched()
     return idx, zq, zr
+
+
+def cast_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[r, :] = cast(src[r, :]) zero-padded to dst's row length (f32 source, f32 / bf16 destination)."""
+    assert src.dtype == torch.float32 and src.dim() == 2 and dst.dim() == 2 and src.stride(1) == 1 and dst.stride(1) == 1
+    assert dst.shape[0] == src.shape[0] and dst.shape[1] >= src.shape[1]
+    _check(require_device().fdm_cast_rows(_ptr(src), src.stride(0), _ptr(dst), _dt(dst), dst.stride(0), src.shape[0],
+                                          src.shape[1], _stream()))
+    _launched()
+    return dst
+
+
+def audio_normalize_pad(audio: torch.Tensor, pad_samples: int = 0, eps: float = 1e-7) -> torch.Tensor:
+    """Wav2Vec2Processor normalisation + zero tail on device (demo/demo_3d_mead.py:85-97). audio (B, L) f32."""
+    assert audio.dtype == torch.float32 and audio.dim() == 2 and audio.is_contiguous()
+    B, L = audio.shape
+    out = torch.empty(B, L + pad_samples, device=audio.device, dtype=torch.float32)
+    _check(require_device().fdm_audio_normalize_pad(_ptr(audio), B, L, _ptr(out), L + pad_samples, eps, _stream()))
+    _launched()
+    return out
+
+
+def vertex_error(pred: torch.Tensor, gt: Optional[torch.Tensor], vertex_idx: Optional[torch.Tensor] = None,
+                 mode: str = "max") -> torch.Tensor:
+    """Per-frame max / mean over a vertex subset of the squared L2 error (metric/metric.py:115-138).
+    pred, gt: (frames, V*3) or (frames, V, 3) f32; returns (frames,) f32 — the metric is its mean."""
+    assert pred.dtype == torch.float32 and pred.is_contiguous()
+    F_ = pred.shape[0]
+    V = pred.numel() // F_ // 3
+    if gt is not None:
+        assert gt.dtype == torch.float32 and gt.is_contiguous() and gt.numel() == pred.numel()
+    if vertex_idx is not None:
+        assert vertex_idx.dtype == torch.int64 and vertex_idx.is_contiguous()
+    out = torch.empty(F_, device=pred.device, dtype=torch.float32)
+    _check(require_device().fdm_vertex_error(_ptr(pred), _ptr(gt), F_, V, _ptr(vertex_idx),
+                                             vertex_idx.numel() if vertex_idx is not None else 0,
+                                             0 if mode == "max" else 1, _ptr(out), _stream()))
+    _launched()
+    return out
 
 
 def cast(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:

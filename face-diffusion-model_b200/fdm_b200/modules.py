@@ -516,8 +516,12 @@ class VQAutoEncoderBase(nn.Module):
             self.__dict__["_engine"] = eng
         return eng
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("EVQ-VAE encode is outside the sampling hot path (SURVEY.md §8(f) item 3)")
+    @torch.no_grad()
+    def encode(self, x, one_hot=None):
+        """x (B, T, in_dim) motion (template subtracted) -> (B, fq*T, zquant_dim) fp32, the tensor quant() takes
+        (reference: models/vq_vae_emotion.py:20-26, models/vq_vae.py:20-26, models/vq_vae_vocaset.py:23-28; for the
+        vocaset / biwi classes the second argument is the unused `x_a`). SURVEY.md section 8(f) item 3."""
+        return self.engine().encode_rows(x, one_hot if self.emotion_sliced else None)
 
     @torch.no_grad()
     def quant(self, x, one_hot=None):

@@ -203,6 +203,21 @@ int fdm_transpose_bcl_to_blc(const float* src, void* dst, int32_t dst_dtype,
  * replicated edge rows (mode 1, Conv1d padding_mode='replicate') or zeros (mode 0). */
 int fdm_pad_time(const void* src, int64_t src_t_stride, void* dst, int32_t dtype, int64_t B, int64_t T,
                  int64_t C, int64_t pad_l, int64_t pad_r, int32_t mode, void* stream);
+/* dst[r, :] = cast(src[r, 0:cols]) then zeros up to ld_dst: gives activations whose row length is not a multiple of
+ * 8 (in_dim = 15069 / 70110 of the EVQ-VAE encoder's first Linear) the 16-byte row pitch the TMA-fed GEMM needs. */
+int fdm_cast_rows(const float* src, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
+                  int64_t rows, int64_t cols, void* stream);
+/* Audio front-end of the demos (demo/demo_3d_mead.py:85-97): Wav2Vec2Processor's zero-mean / unit-variance
+ * normalisation per clip ((x - mean) / sqrt(var + eps), population variance, eps = 1e-7) followed by Lout - L zero
+ * samples (the demos append one second). audio [B, L] f32 -> out [B, Lout] f32. */
+int fdm_audio_normalize_pad(const float* audio, int64_t B, int64_t L, float* out, int64_t Lout, float eps,
+                            void* stream);
+/* Vertex-error metrics of metric/metric.py:115-138 on device: for every frame, reduce over the vertices
+ * vertex_idx[0..n_idx) (NULL: all V vertices) the squared L2 distance between pred and gt ([frames, V, 3] f32;
+ * gt == NULL compares against zeros): mode 0 = max (LVE / FVE / all-vertex error), mode 1 = mean (EME).
+ * out_per_frame [frames] f32; the metric is its mean over frames. */
+int fdm_vertex_error(const float* pred, const float* gt, int64_t frames, int64_t V, const int64_t* vertex_idx,
+                     int64_t n_idx, int32_t mode, float* out_per_frame, void* stream);
 /* Audio feature-encoder layer 0: Conv1d(1, C, k=10, stride=5, optional bias) on raw audio, then
  * LayerNorm(C) + GELU (ln_g != NULL: hubert-large "layer" variant) or nothing (ln_g == NULL: wav2vec2-base "group"
  * variant, normalised over time afterwards by fdm_leaky_instnorm).

@@ -270,6 +270,45 @@ def vq_decode(sd: Dict[str, torch.Tensor], preset: str, zq: torch.Tensor, n_laye
     return F.linear(x, sd[p + "vertice_map_reverse.weight"], sd.get(p + "vertice_map_reverse.bias"))
 
 
+# ---- E1: VQ-VAE encoder for one clip ---------------------------------------------
+def vq_encode(sd: Dict[str, torch.Tensor], preset: str, verts: torch.Tensor, emo_one_hot: Optional[torch.Tensor] = None,
+              n_layers: int = 6, heads: int = 8) -> torch.Tensor:
+    """verts (T, in_dim) motion (template already subtracted) -> latent rows (fq*T, D) as VQAutoEncoder.encode returns
+    them for B = 1. models/vq_vae_emotion.py:20-26,131-197 (emotion_mapping added to every frame),
+    models/vq_vae.py:20-26,133-195, models/vq_vae_vocaset.py:23-28,131-191 (no encoder_linear_embedding_post in its
+    forward); blocks as in models/lib/base_models.py:37-174,286-301."""
+    P = PRESETS[preset]
+    fq, D = P["fq"], P["zdim"]
+    p = "encoder."
+    x = F.leaky_relu(F.linear(verts, sd[p + "vertice_mapping.0.weight"], sd[p + "vertice_mapping.0.bias"]), 0.2)
+    if P["emotion"]:
+        e = F.leaky_relu(F.linear(emo_one_hot.reshape(1, -1), sd[p + "emotion_mapping.0.weight"], sd[p + "emotion_mapping.0.bias"]), 0.2)
+        x = x + e
+    h = x.t()[None]
+    h = F.conv1d(F.pad(h, (2, 2), mode="replicate"), sd[p + "squasher.0.0.weight"], sd[p + "squasher.0.0.bias"])
+    h = F.instance_norm(F.leaky_relu(h, 0.2), eps=1e-5)
+    x = h[0].t()
+    x = F.linear(x, sd[p + "encoder_linear_embedding.net.weight"], sd[p + "encoder_linear_embedding.net.bias"])
+    d = x.shape[-1]
+    x = x + sin_pe(1, d)[0]  # pe[:B] with B = 1 (base_models.py:300)
+    dh = d // heads
+    T = x.shape[0]
+    for l in range(n_layers):
+        a = p + f"encoder_transformer.net.{2 * l}.fn."
+        y = F.layer_norm(x, (d,), sd[a + "norm.weight"], sd[a + "norm.bias"], 1e-5)
+        qkv = F.linear(y, sd[a + "fn.to_qkv.weight"]).view(T, 3, heads, dh).permute(1, 2, 0, 3)
+        dots = (qkv[0] @ qkv[1].transpose(-1, -2)) * (d ** -0.5)
+        o = (torch.softmax(dots, -1) @ qkv[2]).permute(1, 0, 2).reshape(T, d)
+        x = x + F.linear(o, sd[a + "fn.to_out.weight"], sd[a + "fn.to_out.bias"])
+        m = p + f"encoder_transformer.net.{2 * l + 1}.fn."
+        y = F.layer_norm(x, (d,), sd[m + "norm.weight"], sd[m + "norm.bias"], 1e-5)
+        x = x + F.linear(_gelu_tanh(F.linear(y, sd[m + "fn.l1.weight"], sd[m + "fn.l1.bias"])), sd[m + "fn.l2.weight"],
+                         sd[m + "fn.l2.bias"])
+    if preset != "vocaset":
+        x = F.linear(x, sd[p + "encoder_linear_embedding_post.net.weight"], sd[p + "encoder_linear_embedding_post.net.bias"])
+    return x.reshape(T * fq, D)
+
+
 # ---- A1: audio encoder (third-party arithmetic: installed `transformers`) -------------------------------
 def audio_encoder_config(kind: str, tiny: bool = False):
     from transformers import HubertConfig, Wav2Vec2Config

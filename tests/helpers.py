@@ -75,3 +75,35 @@ def hf_audio_model(preset: str, sd, tiny=True):
     m = cls(R.audio_encoder_config(kind, tiny)).eval()
     m.load_state_dict({k[len("audio_encoder."):]: v for k, v in sd.items() if k.startswith("audio_encoder.")})
     return m
+
+
+def build_vqvae(preset: str, device="cpu", codebook="normal"):
+    """Product EVQ-VAE alone (same constructor a reference user calls), parity weights loaded."""
+    from oracle.weights import fill_state_dict
+    warnings.simplefilter("ignore")
+    if preset == "vocaset":
+        from models.vq_vae_vocaset import VQAutoEncoder
+        from models.utils.config import vocaset_vq_vae_args as vargs
+    elif preset == "mead":
+        from models.vq_vae_emotion import VQAutoEncoder
+        from utiles.args import vq_vae_args as vargs
+    else:
+        from models.vq_vae import VQAutoEncoder
+        from models.utils.config import biwi_vq_vae_args as vargs
+    ae = VQAutoEncoder(vargs())
+    ae.load_state_dict(fill_state_dict(ae.state_dict(), SEED, codebook=codebook))
+    return ae.eval().to(device)
+
+
+def encoder_case(preset: str, ae=None):
+    """(EVQ-VAE state_dict on CPU, motion (T, in_dim), emotion one-hot | None, reference encode() output (fq*T, D)) —
+    the seeded input of oracle/gen_golden_encode.py and the output the real reference produced for it."""
+    from oracle import reference_ops as R
+    g = golden("encode")
+    T = int(g["frames"])
+    gen = torch.Generator(device="cpu").manual_seed(4321 + len(preset))
+    x = torch.randn(T, R.PRESETS[preset]["in_dim"], generator=gen)
+    emo = torch.eye(7)[4][None] if R.PRESETS[preset]["emotion"] else None
+    ae = ae if ae is not None else build_vqvae(preset)
+    sd = {k: v.detach().cpu() for k, v in ae.state_dict().items()}
+    return sd, x, emo, torch.from_numpy(g[f"{preset}_h"])

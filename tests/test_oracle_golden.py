@@ -112,3 +112,15 @@ def test_philox_reference_statistics():
     assert [int(v[0]) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     z = philox_normal(1234, 3, 17, 1 << 16)
     assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_oracle_vq_encode(preset):
+    """The encoder restatement against the outputs of the reference's VQAutoEncoder.encode (oracle/gen_golden_encode.py)."""
+    import numpy as np
+    from helpers import encoder_case
+    from oracle import reference_ops as R
+    sd, x, emo, want = encoder_case(preset)
+    got = R.vq_encode(sd, preset, x, emo)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())

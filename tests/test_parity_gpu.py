@@ -2,6 +2,7 @@
 vectors recorded from the real reference. Tolerances are the ones BASELINE.json's north_star states:
 fp32 mode 1e-4 max-abs on final vertices; bf16 mode 2e-2 relative on the per-step denoiser output; VQ indices
 bit-exact against the defined fp32 argmin."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -198,3 +199,60 @@ def test_philox_device_matches_host_reference(cuda_dev):
     lib.philox_normal(out, seed=0x1234ABCD5678, clip_index0=5, t=321)
     ref = np.stack([philox_normal(0x1234ABCD5678, 5 + b, 321, 4096) for b in range(2)])
     assert np.abs(out.cpu().numpy() - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vq_encode_vs_reference_golden(cuda_dev, preset, precision):
+    """VQAutoEncoder.encode on the CUDA path against what the real reference produced (tests/golden/encode.npz):
+    fp32 mode within 1e-4 (relative to max(1, |ref|)), bf16 mode within 2e-2 relative L2; then encode -> quant must give
+    the oracle's indices for the fp32 latent. Also checks batch == per-clip."""
+    from helpers import build_vqvae, encoder_case
+    from oracle import reference_ops as R  # checker
+    ae = build_vqvae(preset, device=cuda_dev)
+    ae.set_precision(precision)
+    sd, x, emo, want = encoder_case(preset, ae)
+    args = (x[None].to(cuda_dev),) + ((emo.to(cuda_dev),) if emo is not None else ())
+    h = ae.encode(*args)
+    torch.cuda.synchronize()
+    assert h.shape == (1,) + tuple(want.shape) and h.dtype == torch.float32
+    if precision == "fp32":
+        err = (h[0].cpu() - want).abs().max().item() / max(1.0, want.abs().max().item())
+        assert err < 1e-4, err
+        zq, _, (_, _, idx) = ae.quant(h, *args[1:])
+        emo_pos = int(torch.argmax(emo)) if emo is not None else None
+        oi, _, _ = R.vq_quantize(h[0].cpu(), sd["quantize.embedding.weight"], emo_pos)
+        assert torch.equal(oi, idx[:, 0].cpu())
+    else:
+        rel = ((h[0].cpu() - want).norm() / want.norm()).item()
+        assert rel < 2e-2, rel
+    xb = torch.stack([x, x.flip(0)]).to(cuda_dev)
+    hb = ae.encode(xb, *( (emo.to(cuda_dev).expand(2, -1),) if emo is not None else ()))
+    assert torch.equal(hb[0], h[0])
+
+
+def test_audio_frontend_and_vertex_metrics(cuda_dev):
+    """Wav2Vec2Processor normalisation + 1 s pad, and the LVE / FVE / EME formulas of
+    metric/metric.py, on device against their numpy statements."""
+    import numpy as np
+    from fdm_b200.frontend import prepare_audio, vertex_metrics
+    from helpers import GOLDEN
+    g = torch.Generator(device="cpu").manual_seed(3)
+    speech = torch.randn(3, 64000, generator=g) * torch.tensor([0.01, 1.0, 30.0])[:, None] + torch.tensor([0.5, 0.0, -2.0])[:, None]
+    out = prepare_audio(speech.to(cuda_dev)).cpu().numpy()
+    for b in range(3):
+        x = speech[b].numpy()
+        ref = (x - x.mean()) / np.sqrt(x.var() + 1e-7)  # transformers Wav2Vec2FeatureExtractor.zero_mean_unit_var_norm
+        ref = np.concatenate((ref, np.zeros(16000, np.float32)))
+        assert out[b].shape == ref.shape and np.abs(out[b] - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    lip = np.load(os.path.join(GOLDEN, "lip_vertices.npy"))
+    pred, gt = torch.randn(50, 15069, generator=g), torch.randn(50, 15069, generator=g)
+    face = np.arange(100, 2100)
+    got = vertex_metrics(pred.to(cuda_dev), gt.to(cuda_dev), lip_idx=torch.from_numpy(lip), face_idx=torch.from_numpy(face),
+                         emotion_idx=torch.from_numpy(face[::2].copy()))
+    P, G = pred.numpy().reshape(50, -1, 3), gt.numpy().reshape(50, -1, 3)
+    d2 = np.sum(np.square(G - P), axis=2)
+    want = {"all": d2.max(1).mean(), "lve": d2[:, lip].max(1).mean(), "fve": d2[:, face].max(1).mean(),
+            "eme": d2[:, face[::2]].mean(1).mean()}
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-5 * abs(v), (k, got[k], v)
