@@ -177,6 +177,8 @@ def profile_step(eng, sampler_args, repeats=3):
         return inner
 
     x_in, t_dev, ddpm = sampler_args
+    lanes = getattr(eng, "lanes", 1)
+    eng.lanes = 1  # serial launches on one stream: the per-kernel events must not overlap another lane's kernels
     try:
         for n in orig:
             setattr(lib, n, wrap(n))
@@ -185,6 +187,7 @@ def profile_step(eng, sampler_args, repeats=3):
             ddpm(x0)
         torch.cuda.synchronize()
     finally:
+        eng.lanes = lanes
         for n, fn in orig.items():
             setattr(lib, n, fn)
     agg = {}
@@ -438,6 +441,7 @@ def main():
             "config": {"workload": workload, "global_clips": world * B, "frames_per_clip": T, "ddpm_steps": args.ddpm_steps,
                        "guidance": 2.5 if use_cfg else None, "noise": "in-kernel Philox4x32-10 keyed by global clip index",
                        "parallelism": f"dp{world} (clips sharded, one all-gather of vertices)",
+                       "denoiser_lanes": (fdm.engine().lanes if use_cfg else 1),
                        "l2": "inputs larger than L2: every denoise step streams > 1.4 GB of activations, weights and cross-attention "
                              "caches through the 126 MB L2, each job starts from fresh input tensors and ends with a 764 MB vertex "
                              "write; no explicit flush is needed between timed jobs"},
