@@ -47,6 +47,8 @@ class DenoiserEngine:
         self.passes = 1
         self.lanes = int(os.environ.get("FDM_B200_LANES", "1"))
         self._side = None
+        self._pool = {}          # name -> persistent device buffer (stable addresses keep captured step graphs valid)
+        self.graph_cache = {}    # sampler step graphs, keyed by every address / scalar baked into them
 
     # ---- weights ---------------------------------------------------------------------------------
     def _params(self):
@@ -106,6 +108,17 @@ class DenoiserEngine:
         self._packed_key = key
         self.pack_serial += 1
 
+    def buf(self, name: str, shape, dtype, device=None) -> torch.Tensor:
+        """Persistent buffer: the same tensor is returned while name / shape / dtype / device do not change, so that a
+        new clip batch of the same shape reuses the addresses the cached CUDA graphs were captured with."""
+        device = device if device is not None else self.dev
+        t = self._pool.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+            with torch.inference_mode(False):  # a normal tensor: it is updated in place inside and outside inference mode
+                t = torch.empty(tuple(shape), device=device, dtype=dtype)
+            self._pool[name] = t
+        return t
+
     # ---- per-clip-batch state ---------------------------------------------------------------------
     def prepare(self, audio_hidden: torch.Tensor, n_frames: int, id_one_hot: torch.Tensor,
                 emo_one_hot: Optional[torch.Tensor] = None, guidance: Optional[str] = None) -> None:
@@ -126,15 +139,15 @@ class DenoiserEngine:
         a = a.reshape(B * T, P.audio_in) if a.is_contiguous() else a.contiguous().view(B * T, P.audio_in)
         dev, dt = self.dev, self.dtype
         BT = B * T
-        h = torch.empty(BT, d, device=dev, dtype=dt)
-        af = torch.empty(BT, d, device=dev, dtype=dt)
+        h = self.buf("prep_h", (BT, d), dt)
+        af = self.buf("prep_af", (BT, d), dt)
         lib.gemm(a, w["ae0_w"], h, bias=w["ae0_b"], act=lib.ACT_MISH)
         lib.gemm(h, w["ae2_w"], af, bias=w["ae2_b"])
         # audio part of the collapsed cross-attention, per layer
         self.cross = []
         for l in range(P.layers):
             L = w[l]
-            c = torch.empty(BT, d, device=dev, dtype=dt)
+            c = self.buf(f"cross{l}", (BT, d), dt)
             lib.gemm(af, L["cv_w"], h, bias=L["cv_b"])
             lib.gemm(h, L["co_w"], c, bias=L["co_b"])
             self.cross.append(c)
@@ -162,16 +175,18 @@ class DenoiserEngine:
             lib.gemm(i_oh, w["st_w"], sty, bias=w["st_b"], act=lib.ACT_MISH if P.style_mish else lib.ACT_NONE)
             if P.emotion:
                 lib.gemm(e_oh, w["em_w"], sty, bias=w["em_b"], residual=sty)
-            addends.append((sty[:, None, :] + pe[None]).to(dt).reshape(BT, d).contiguous())  # setup-time broadcast
+            ad = self.buf(f"addend{len(addends)}", (BT, d), dt)
+            ad.copy_((sty[:, None, :] + pe[None]).reshape(BT, d))  # setup-time broadcast (+ cast)
+            addends.append(ad)
         self.addend = addends
         S = len(passes)
         self.B, self.T, self.passes = B, T, S
-        self.x = torch.empty(S * BT, d, device=dev, dtype=dt)
-        self.qkv = torch.empty(S * BT, 3 * d, device=dev, dtype=dt)
-        self.att = torch.empty(S * BT, d, device=dev, dtype=dt)
-        self.proj = torch.empty(S * BT, d, device=dev, dtype=dt)
-        self.ffn = torch.empty(S * BT, 2 * d, device=dev, dtype=dt)
-        self.x0 = torch.empty(S, B, T * d, device=dev, dtype=torch.float32)
+        self.x = self.buf("x", (S * BT, d), dt)
+        self.qkv = self.buf("qkv", (S * BT, 3 * d), dt)
+        self.att = self.buf("att", (S * BT, d), dt)
+        self.proj = self.buf("proj", (S * BT, d), dt)
+        self.ffn = self.buf("ffn", (S * BT, 2 * d), dt)
+        self.x0 = self.buf("x0", (S, B, T * d), torch.float32)
 
     # ---- one denoiser evaluation ------------------------------------------------------------------------
     def denoise(self, x_in: torch.Tensor, t_dev: torch.Tensor) -> torch.Tensor:
