@@ -31,7 +31,7 @@ void fdm_set_error(const char* fmt, ...);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int fdm_sm_count();  // cached multiprocessor count of the current device
-bool fdm_pdl_enabled();  // programmatic dependent launch for the hot-loop kernels (opt-in: env FDM_B200_PDL=1)
+bool fdm_pdl_enabled();  // programmatic dependent launch for the hot-loop kernels (on by default; env FDM_B200_PDL=0 turns it off)
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------
 // Hot-loop kernels are launched with programmaticStreamSerialization: kernel N+1 may be scheduled while kernel N
