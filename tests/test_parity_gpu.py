@@ -256,3 +256,35 @@ def test_audio_frontend_and_vertex_metrics(cuda_dev):
             "eme": d2[:, face[::2]].mean(1).mean()}
     for k, v in want.items():
         assert abs(got[k] - v) <= 1e-5 * abs(v), (k, got[k], v)
+
+
+def test_cached_step_graphs_are_reused_and_keyed(cuda_dev):
+    """Step graphs are cached per batch shape on the denoiser engine (persistent buffers, stable addresses): a second job
+    of the same shape must replay the cached graph and reproduce a freshly captured run bit for bit, new audio must give
+    new results through the same graph, and anything baked into the graph nodes (the Philox seed) must miss the cache."""
+    from oracle.weights import host_noise
+    clips = (0, 1)
+    fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup("vocaset", cuda_dev, "bf16", clips=clips)
+    T = hiddens[0].shape[0]
+    shape = (len(clips), T * P["fq"], P["zdim"])
+    xT = torch.stack([host_noise(99, c, 1000, shape[1:]) for c in clips]).to(cuda_dev)
+    steps = list(range(999, 975, -1))  # 24 steps: two 10-step replays + 4 single-step replays
+    diff.noise_source, diff.seed = "philox", 5
+    eng = fdm.engine()
+    eng.graph_cache.clear()
+    a = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)
+    assert len(eng.graph_cache) == 1
+    b = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)  # new audio tensor: prepare() runs again
+    assert len(eng.graph_cache) == 1 and torch.equal(a, b)
+    c = diff.p_sample_loop(shape, (audio * 0.5).contiguous(), idh, x_T=xT, steps=steps)
+    assert len(eng.graph_cache) == 1 and not torch.equal(a, c)
+    diff.seed = 6
+    d = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)
+    assert len(eng.graph_cache) == 2 and not torch.equal(a, d)
+    diff.seed = 5
+    eng.graph_cache.clear()
+    e = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)  # fresh capture
+    assert torch.equal(a, e)
+    diff.use_cuda_graph = False
+    f = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)  # eager launches
+    assert torch.equal(a, f)
