@@ -233,26 +233,36 @@ def cpu_reference_sample(args, n_ddpm_steps):
             h = R.audio_encode(hf, audio)  # the reference re-runs the audio encoder in every forward
             return R.fdm_forward(sd, args.preset, h, t, z, idh_, emo_)
 
-        def step(z, t):
+        def denoise_hoisted(z, t, idh_, emo_):  # the same port with the encoder run once per clip
+            return R.fdm_forward(sd, args.preset, hidden, t, z, idh_, emo_)
+
+        def step(z, t, den):
             if args.no_cfg:
-                x0 = denoise_as_is(z, t, idh, emo)
+                x0 = den(z, t, idh, emo)
             elif P["emotion"]:
-                x0 = R.cfg_forward(lambda oh: denoise_as_is(z, t, idh, oh), emo, 2.5)
+                x0 = R.cfg_forward(lambda oh: den(z, t, idh, oh), emo, 2.5)
             else:
-                x0 = R.cfg_forward(lambda oh: denoise_as_is(z, t, oh, None), idh, 2.5)
+                x0 = R.cfg_forward(lambda oh: den(z, t, oh, None), idh, 2.5)
             return R.p_sample(tabs, x0, z, t, torch.randn_like(z))
 
-        step(x, 999)  # warm-up
+        step(x, 999, denoise_as_is)  # warm-up
         t0 = time.perf_counter()
         for i in range(n_ddpm_steps):
-            x = step(x, 998 - i)
+            x = step(x, 998 - i, denoise_as_is)
         per_step = (time.perf_counter() - t0) / n_ddpm_steps
+        # the baseline is reported "as is" and with the audio encoder hoisted out of the loop
+        t0 = time.perf_counter()
+        for i in range(n_ddpm_steps):
+            x = step(x, 998 - n_ddpm_steps - i, denoise_hoisted)
+        per_step_hoisted = (time.perf_counter() - t0) / n_ddpm_steps
         t0 = time.perf_counter()
         idx, zq, _ = R.vq_quantize(x, ae.quantize.embedding.weight.detach(), 4 if P["emotion"] else None)
         R.vq_decode({k: v.detach() for k, v in ae.state_dict().items()}, args.preset, zq)
         tail = time.perf_counter() - t0
     total = per_step * args.ddpm_steps + tail
-    return T / total, dict(s_per_ddpm_step=per_step, quant_decode_s=tail, frames=T, cores=torch.get_num_threads())
+    hoisted_total = per_step_hoisted * args.ddpm_steps + tail + per_step - per_step_hoisted  # one encoder run
+    return T / total, dict(s_per_ddpm_step=per_step, quant_decode_s=tail, frames=T, cores=torch.get_num_threads(),
+                           s_per_ddpm_step_hoisted=per_step_hoisted, fps_hoisted=T / hoisted_total)
 
 
 def main():
@@ -282,7 +292,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * detail["frames"] / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "impl": "oracle port of the reference PyTorch path on host cores"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": detail["cores"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": detail["cores"], "kind": "port", "sample": sample,
+                             "audio_encoder_hoisted": {"value": detail["fps_hoisted"], "unit": UNIT,
+                                                       "s_per_ddpm_step": detail["s_per_ddpm_step_hoisted"]}},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -431,7 +443,9 @@ def main():
         cpu_base = {"value": fps, "unit": UNIT, "cores": detail["cores"], "kind": "port",
                     "sample": (f"oracle port, 1 clip x {args.seconds:g} s, {args.ref_sample_steps} DDPM steps as the reference runs them "
                                f"(audio encoder re-run per denoiser call, guidance = 2 calls/step) + quantise + decode, extrapolated to "
-                               f"{args.ddpm_steps} steps; {detail['s_per_ddpm_step']:.3f} s/step")}
+                               f"{args.ddpm_steps} steps; {detail['s_per_ddpm_step']:.3f} s/step"),
+                    "audio_encoder_hoisted": {"value": detail["fps_hoisted"], "unit": UNIT, "s_per_ddpm_step": detail["s_per_ddpm_step_hoisted"],
+                                              "note": "same port with the audio encoder run once per clip instead of in every denoiser call"}}
 
     if rank == 0:
         line = {
