@@ -40,53 +40,79 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t clip, u
   const float u3 = static_cast<float>(r[3] >> 8) * inv24;
   const float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
   float sa, ca, sb, cb;
-  sincosf(6.283185307179586f * u1, &sa, &ca);
-  sincosf(6.283185307179586f * u3, &sb, &cb);
+  sincospif(2.f * u1, &sa, &ca);  // sin / cos of 2 pi u without the range reduction of sincosf
+  sincospif(2.f * u3, &sb, &cb);
   return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
 }
 
-__global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, const int64_t n4, const int64_t e4_per_clip) {
+// grid = (chunks, clips): a block walks one clip's float4 elements, two per thread and iteration (six 16-byte loads in
+// flight before the Philox / Box-Muller arithmetic), so no 64-bit division sits in the loop and t / c1 / c2 / sigma are
+// per-block constants.
+__device__ __forceinline__ float4 ddpm_update(const fdm_ddpm_args& a, float4 x0, const float4& u, const float4& xt, float c1, float c2) {
+  if (a.x0_uncond) {
+    // u + s*(c - u), each op rounded separately (utiles/classifierfree.py:20-21)
+    x0.x = __fadd_rn(u.x, __fmul_rn(a.guidance, __fsub_rn(x0.x, u.x)));
+    x0.y = __fadd_rn(u.y, __fmul_rn(a.guidance, __fsub_rn(x0.y, u.y)));
+    x0.z = __fadd_rn(u.z, __fmul_rn(a.guidance, __fsub_rn(x0.z, u.z)));
+    x0.w = __fadd_rn(u.w, __fmul_rn(a.guidance, __fsub_rn(x0.w, u.w)));
+  }
+  float4 o;
+  o.x = __fadd_rn(__fmul_rn(c1, x0.x), __fmul_rn(c2, xt.x));
+  o.y = __fadd_rn(__fmul_rn(c1, x0.y), __fmul_rn(c2, xt.y));
+  o.z = __fadd_rn(__fmul_rn(c1, x0.z), __fmul_rn(c2, xt.z));
+  o.w = __fadd_rn(__fmul_rn(c1, x0.w), __fmul_rn(c2, xt.w));
+  return o;
+}
+__device__ __forceinline__ void ddpm_store(const fdm_ddpm_args& a, int64_t i, float4 o, const float4& z, float sg, bool add_noise) {
+  if (add_noise) {
+    o.x = __fadd_rn(o.x, __fmul_rn(sg, z.x));
+    o.y = __fadd_rn(o.y, __fmul_rn(sg, z.y));
+    o.z = __fadd_rn(o.z, __fmul_rn(sg, z.z));
+    o.w = __fadd_rn(o.w, __fmul_rn(sg, z.w));
+  }
+  reinterpret_cast<float4*>(a.out)[i] = o;
+  if (a.out_bf16) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(o.x, o.y);
+    h[1] = __floats2bfloat162_rn(o.z, o.w);
+    reinterpret_cast<uint2*>(a.out_bf16)[i] = u;
+  }
+}
+
+__global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, const int64_t e4_per_clip) {
   pdl_trigger();
   pdl_wait();
-  const int t_graph = a.t_per_clip ? 0 : *a.t_dev;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t b = i / e4_per_clip;
-    const int t = a.t_per_clip ? static_cast<int>(a.t_per_clip[b]) : t_graph;
-    const float c1 = a.c1[t], c2 = a.c2[t], sg = a.sigma[t];
-    float4 x0 = reinterpret_cast<const float4*>(a.x0_cond)[i];
-    if (a.x0_uncond) {
-      const float4 u = reinterpret_cast<const float4*>(a.x0_uncond)[i];
-      // u + s*(c - u), each op rounded separately (utiles/classifierfree.py:20-21)
-      x0.x = __fadd_rn(u.x, __fmul_rn(a.guidance, __fsub_rn(x0.x, u.x)));
-      x0.y = __fadd_rn(u.y, __fmul_rn(a.guidance, __fsub_rn(x0.y, u.y)));
-      x0.z = __fadd_rn(u.z, __fmul_rn(a.guidance, __fsub_rn(x0.z, u.z)));
-      x0.w = __fadd_rn(u.w, __fmul_rn(a.guidance, __fsub_rn(x0.w, u.w)));
+  const int64_t b = blockIdx.y;
+  const int t = a.t_per_clip ? static_cast<int>(a.t_per_clip[b]) : *a.t_dev;
+  const float c1 = a.c1[t], c2 = a.c2[t], sg = a.sigma[t];
+  const bool add_noise = t > 0;
+  const uint32_t clip = static_cast<uint32_t>(a.clip_index0 + b);
+  const int64_t base = b * e4_per_clip;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e0 < e4_per_clip; e0 += 2 * stride) {
+    const int64_t e1 = e0 + stride;
+    const bool two = e1 < e4_per_clip;
+    const int64_t i0 = base + e0, i1 = base + (two ? e1 : e0);
+    const float4 xa = reinterpret_cast<const float4*>(a.x0_cond)[i0];
+    const float4 xb = reinterpret_cast<const float4*>(a.x0_cond)[i1];
+    const float4 ua = a.x0_uncond ? reinterpret_cast<const float4*>(a.x0_uncond)[i0] : zero;
+    const float4 ub = a.x0_uncond ? reinterpret_cast<const float4*>(a.x0_uncond)[i1] : zero;
+    const float4 ta = reinterpret_cast<const float4*>(a.x_t)[i0];
+    const float4 tb = reinterpret_cast<const float4*>(a.x_t)[i1];
+    float4 za = zero, zb = zero;
+    if (add_noise) {
+      if (a.noise) {
+        za = reinterpret_cast<const float4*>(a.noise)[i0];
+        zb = reinterpret_cast<const float4*>(a.noise)[i1];
+      } else {
+        za = philox_normal4(a.seed, clip, static_cast<uint32_t>(t), static_cast<uint64_t>(e0));
+        if (two) zb = philox_normal4(a.seed, clip, static_cast<uint32_t>(t), static_cast<uint64_t>(e1));
+      }
     }
-    const float4 xt = reinterpret_cast<const float4*>(a.x_t)[i];
-    float4 o;
-    o.x = __fadd_rn(__fmul_rn(c1, x0.x), __fmul_rn(c2, xt.x));
-    o.y = __fadd_rn(__fmul_rn(c1, x0.y), __fmul_rn(c2, xt.y));
-    o.z = __fadd_rn(__fmul_rn(c1, x0.z), __fmul_rn(c2, xt.z));
-    o.w = __fadd_rn(__fmul_rn(c1, x0.w), __fmul_rn(c2, xt.w));
-    if (t > 0) {
-      float4 z;
-      if (a.noise) z = reinterpret_cast<const float4*>(a.noise)[i];
-      else z = philox_normal4(a.seed, static_cast<uint32_t>(a.clip_index0 + b), static_cast<uint32_t>(t),
-                              static_cast<uint64_t>(i - b * e4_per_clip));
-      o.x = __fadd_rn(o.x, __fmul_rn(sg, z.x));
-      o.y = __fadd_rn(o.y, __fmul_rn(sg, z.y));
-      o.z = __fadd_rn(o.z, __fmul_rn(sg, z.z));
-      o.w = __fadd_rn(o.w, __fmul_rn(sg, z.w));
-    }
-    reinterpret_cast<float4*>(a.out)[i] = o;
-    if (a.out_bf16) {
-      uint2 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-      h[0] = __floats2bfloat162_rn(o.x, o.y);
-      h[1] = __floats2bfloat162_rn(o.z, o.w);
-      reinterpret_cast<uint2*>(a.out_bf16)[i] = u;
-    }
+    ddpm_store(a, i0, ddpm_update(a, xa, ua, ta, c1, c2), za, sg, add_noise);
+    if (two) ddpm_store(a, i1, ddpm_update(a, xb, ub, tb, c1, c2), zb, sg, add_noise);
   }
 }
 
@@ -160,9 +186,15 @@ extern "C" int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream) {
                        reinterpret_cast<uintptr_t>(a.x_t) | reinterpret_cast<uintptr_t>(a.noise) |
                        reinterpret_cast<uintptr_t>(a.out);
   FDM_CHECK_ARG(al % 16 == 0 && reinterpret_cast<uintptr_t>(a.out_bf16) % 8 == 0, "fdm_ddpm_step: operands must be 16-byte aligned");
-  const int64_t n4 = a.B * a.elems_per_clip / 4;
-  FDM_CHECK_CUDA(fdm_launch_pdl(ddpm_step_kernel, dim3(grid_for(n4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, a, n4,
-                                a.elems_per_clip / 4));
+  FDM_CHECK_ARG(a.B <= 65535, "fdm_ddpm_step: at most 65535 clips per call");
+  const int64_t e4 = a.elems_per_clip / 4;
+  // ~8 resident 256-thread CTAs per SM over the whole batch, two float4 per thread and iteration
+  int64_t gx = ceil_div64(static_cast<int64_t>(fdm_sm_count()) * 8, a.B);
+  const int64_t gx_max = ceil_div64(e4, 512);
+  if (gx > gx_max) gx = gx_max;
+  if (gx < 1) gx = 1;
+  FDM_CHECK_CUDA(fdm_launch_pdl(ddpm_step_kernel, dim3(static_cast<unsigned>(gx), static_cast<unsigned>(a.B)), dim3(256), 0,
+                                reinterpret_cast<cudaStream_t>(stream), 1, a, e4));
   return 0;
 }
 
