@@ -60,4 +60,24 @@ for algo, name in ((lib.VQ_FFMA, "ffma"), (lib.VQ_TENSOR, "tensor")):
                             "recheck_row_fraction": (cnt.item() / rows) if algo == lib.VQ_TENSOR else None,
                             "bit_exact_vs_oracle": ok, "rows_checked_vs_oracle": 2 * n_chk})
 out["tensor_equals_ffma_all_rows"] = bool(torch.equal(all_idx["ffma"], all_idx["tensor"]))
+# HBM GB/s sweep over the batch size (tensor-core path, indices + z_q (B, D, L))
+out["sweep"] = []
+for n in (1, 4, 16, 64, 256, 1024):
+    if n > clips:
+        break
+    zs = z[:n]
+    for _ in range(3):
+        lib.vq_quantize(zs, cb, codes, want_bdl=True, algo=lib.VQ_TENSOR)
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        lib.vq_quantize(zs, cb, codes, want_bdl=True, algo=lib.VQ_TENSOR)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg = n * L * (4 * D + 8 + 4 * D)
+    out["sweep"].append({"clips": n, "rows": n * L, "ms": ms, "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
+                         "frac_of_hbm_peak": alg / (ms / 1e3) / 1e9 / peak,
+                         "note": "< 64 clips the input fits the 126 MB L2 and the loop re-reads it from there" if n * L * 256 < 100e6 else ""})
 print(json.dumps(out))
