@@ -53,6 +53,14 @@ struct Epilogue {
   int32_t tma_c, vec_r, vec_bias;  // C through TMA stores; 16-byte vector access legal for residual / bias
   int32_t tma_r;                   // bf16 residual tiles fetched by TMA into the staging tile (needs tma_c, bf16 out)
   int32_t M;
+  // LayerNorm folding (see fdm_gemm_args): consumer correction, residual rebuilt from un-normalised rows, output statistics
+  const float* a_ln;
+  const float* w_colsum;
+  const float* res_ln;
+  const float* res_gamma;
+  const float* res_beta;
+  float* stats_out;
+  int32_t stats_parts;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -230,9 +238,15 @@ __device__ __forceinline__ void act_inplace(float (&v)[32], int act) {
 }
 
 // bias + activation + residual for 32 consecutive columns [col0, col0+32) of output row `row`
-__device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int64_t row, bool row_ok, int col0, int N) {
+__device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int64_t row, bool row_ok, int col0, int N,
+                                              float a_mean = 0.f, float a_rstd = 1.f) {
   const int ncols = min(32, N - col0);
   const bool full = ncols == 32;
+  if (ep.a_ln) {  // A held un-normalised rows: C = rstd (acc - mean * colsum(W')) (+ bias' below)
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) v[j] = a_rstd * fmaf(-a_mean, __ldg(ep.w_colsum + col0 + j), v[j]);
+  }
   if (ep.bias) {
     if (full && ep.vec_bias) {
       const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
@@ -479,11 +493,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + c_begin;
+        const int64_t row = static_cast<int64_t>(row_w) + lane;
+        const bool row_ok = row < M;
+        float r_mean = 0.f, r_rstd = 1.f;
+        if (ep.res_ln && row_ok) {
+          const float2 mr = __ldg(reinterpret_cast<const float2*>(ep.res_ln) + row);
+          r_mean = mr.x;
+          r_rstd = mr.y;
+        }
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c, ++g) {
           const int col0 = n_base + c * 64;
           const uint32_t b = g % NB_STAGE;
           const uint32_t sbuf = stage_base + b * 4096u;
+          float st_s = 0.f, st_q = 0.f;  // sum / sum of squares of this thread's 64 output values (stats_out)
           mbar_wait(res_bar(ew, b), (g / NB_STAGE) & 1u);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -508,12 +531,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint32_t oo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
-                oo[e] = pack2(v[8 * j + 2 * e] + f.x, v[8 * j + 2 * e + 1] + f.y);
+                float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
+                if (ep.res_ln) {  // the residual tile holds un-normalised rows: rebuild LN(u) element-wise
+                  const int col = col0 + half * 32 + 8 * j + 2 * e;
+                  const float2 gm = __ldg(reinterpret_cast<const float2*>(ep.res_gamma + col));
+                  const float2 bt = __ldg(reinterpret_cast<const float2*>(ep.res_beta + col));
+                  f.x = fmaf((f.x - r_mean) * r_rstd, gm.x, bt.x);
+                  f.y = fmaf((f.y - r_mean) * r_rstd, gm.y, bt.y);
+                }
+                const float o0 = v[8 * j + 2 * e] + f.x, o1 = v[8 * j + 2 * e + 1] + f.y;
+                st_s += o0 + o1;
+                st_q = fmaf(o0, o0, fmaf(o1, o1, st_q));
+                oo[e] = pack2(o0, o1);
               }
               st_shared_v4(addr, oo[0], oo[1], oo[2], oo[3]);
             }
           }
+          if (ep.stats_out && row_ok)
+            *reinterpret_cast<float2*>(ep.stats_out + (row * ep.stats_parts + (col0 >> 6)) * 2) = make_float2(st_s, st_q);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -536,6 +571,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row_w = m_blk * (BLOCK_M * CG) + row_in_tile + quad * 32;  // first row of this warp's slab
       const int64_t row = static_cast<int64_t>(row_w) + lane;
       const bool row_ok = row < M;
+      float a_mean = 0.f, a_rstd = 1.f;
+      if (ep.a_ln && row_ok) {
+        const float2 mr = __ldg(reinterpret_cast<const float2*>(ep.a_ln) + row);
+        a_mean = mr.x;
+        a_rstd = mr.y;
+      }
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += CW, ++g) {
@@ -551,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_math(v, ep, row, row_ok, col0, N);
+          epilogue_math(v, ep, row, row_ok, col0, N, a_mean, a_rstd);
           if (out_bf16) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -571,7 +612,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_math(v, ep, row, row_ok, col0 + 32, N);
+          epilogue_math(v, ep, row, row_ok, col0 + 32, N, a_mean, a_rstd);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_shared_v4(sbuf + stage_off(lane, 4 + j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
@@ -734,6 +775,18 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   ep.vec_bias = a.bias && aligned16(a.bias);
   ep.tma_r = ep.tma_c && a.residual && a.res_dtype == FDM_BF16 && a.out_dtype == FDM_BF16 && aligned16(a.residual) &&
              (a.ldr * 2) % 16 == 0;
+  ep.a_ln = a.a_ln;
+  ep.w_colsum = a.w_colsum;
+  ep.res_ln = a.res_ln;
+  ep.res_gamma = a.res_gamma;
+  ep.res_beta = a.res_beta;
+  ep.stats_out = a.stats_out;
+  ep.stats_parts = static_cast<int32_t>(a.N / 64);
+  FDM_CHECK_ARG(!a.a_ln || (a.w_colsum && !ep.tma_r), "fdm_gemm_bf16: a_ln needs w_colsum and a GEMM without the bf16 residual path");
+  FDM_CHECK_ARG(!a.res_ln || (ep.tma_r && a.res_gamma && a.res_beta && a.N % 64 == 0 && aligned16(a.res_gamma) && aligned16(a.res_beta)),
+                "fdm_gemm_bf16: res_ln needs a bf16 residual / bf16 output on the TMA path, res_gamma, res_beta and N %% 64 == 0");
+  FDM_CHECK_ARG(!a.stats_out || (ep.tma_r && a.N % 64 == 0),
+                "fdm_gemm_bf16: stats_out needs the bf16 residual TMA path and N %% 64 == 0");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 
   // Tile width: the widest tile that still yields at least one tile per SM; narrow problems fall to 64.

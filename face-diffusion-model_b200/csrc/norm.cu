@@ -368,3 +368,33 @@ extern "C" int fdm_leaky_instnorm(const void* x, int32_t x_dtype, void* out, int
   FDM_CHECK_LAUNCH();
   return 0;
 }
+
+namespace {
+// one thread per row: (mean, rstd) from the per-column-group partial sums a GEMM epilogue wrote (fixed summation order)
+__global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float* __restrict__ partials, int64_t M, int parts, float inv_d,
+                                                                float eps, float* __restrict__ mean_rstd) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const float2* p = reinterpret_cast<const float2*>(partials) + row * parts;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < parts; ++i) {
+    const float2 v = p[i];
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * inv_d;
+  const float var = fmaxf(q * inv_d - mean * mean, 0.f);
+  reinterpret_cast<float2*>(mean_rstd)[row] = make_float2(mean, 1.f / sqrtf(var + eps));
+}
+}  // namespace
+
+extern "C" int fdm_ln_stats_finalize(const float* partials, int64_t M, int64_t parts, int64_t d, float eps, float* mean_rstd,
+                                     void* stream) {
+  FDM_CHECK_ARG(partials && mean_rstd && M > 0 && parts > 0 && d > 0, "fdm_ln_stats_finalize: bad arguments");
+  const unsigned grid = static_cast<unsigned>(ceil_div64(M, 256));
+  FDM_CHECK_CUDA(fdm_launch_pdl(ln_stats_finalize_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, partials, M,
+                                static_cast<int>(parts), 1.f / static_cast<float>(d), eps, mean_rstd));
+  return 0;
+}

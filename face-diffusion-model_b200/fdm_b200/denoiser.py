@@ -47,6 +47,7 @@ class DenoiserEngine:
         self.passes = 1
         self.lanes = int(os.environ.get("FDM_B200_LANES", "1"))
         self._side = None
+        self.fold = False
         self._pool = {}          # name -> persistent device buffer (stable addresses keep captured step graphs valid)
         self.graph_cache = {}    # sampler step graphs, keyed by every address / scalar baked into them
 
@@ -98,6 +99,23 @@ class DenoiserEngine:
             L["time_cross"] = torch.empty(n_t, d, device=dev)
             lib.gemm(tmp, Bv(p + "multihead_attn.out_proj.weight"), L["time_cross"])
             w[l] = L
+        # LayerNorm folding (bf16 mode): norm3 of layer l-1 is never materialised. The FFN2 GEMM writes u = x + FFN(x) and its
+        # row statistics; the next QKV projection (or the latent decoder after the last layer) runs on u with
+        # W' = W diag(gamma3), colsum(W') and bias' = bias + W beta3, and the out-projection rebuilds LN3(u) for its residual.
+        # Opt-in (FDM_B200_FOLD_LN=1): it removes 0.23 ms of LayerNorm kernels per step but the extra epilogue work (per-column
+        # gamma / beta on a row-per-thread layout, row statistics) costs the GEMMs the same 0.23 ms - 4.64 vs 4.47 ms per step.
+        self.fold = self.dtype == torch.bfloat16 and os.environ.get("FDM_B200_FOLD_LN", "0") == "1"
+        if self.fold:
+            def folded(weight_f32, bias_f32, gamma, beta):
+                wp = (weight_f32 * gamma[None]).to(self.dtype).contiguous()
+                return wp, wp.float().sum(-1).contiguous(), (bias_f32 + weight_f32 @ beta).contiguous()
+            for l in range(1, P.layers):
+                p = f"transformer_decoder.layers.{l}."
+                g3, b3 = w[l - 1]["n3_w"], w[l - 1]["n3_b"]
+                w[l]["qkv_wf"], w[l]["qkv_cs"], w[l]["qkv_bf"] = folded(sd[p + "self_attn.in_proj_weight"].detach().float(),
+                                                                      w[l]["qkv_b"], g3, b3)
+            g3, b3 = w[P.layers - 1]["n3_w"], w[P.layers - 1]["n3_b"]
+            w["ld_wf"], w["ld_cs"], w["ld_bf"] = folded(sd["latent_decoder.weight"].detach().float(), w["ld_b"], g3, b3)
         w["slopes"] = torch.tensor(alibi_slopes(P.heads), dtype=torch.float32, device=dev)
         if P.periodic_pe:
             w["pe"] = _sin_table(P.period, d).to(dev)
@@ -187,6 +205,9 @@ class DenoiserEngine:
         self.proj = self.buf("proj", (S * BT, d), dt)
         self.ffn = self.buf("ffn", (S * BT, 2 * d), dt)
         self.x0 = self.buf("x0", (S, B, T * d), torch.float32)
+        if self.fold:
+            self.ln_parts = self.buf("ln_parts", (S * BT, d // 64, 2), torch.float32)
+            self.ln_mr = self.buf("ln_mr", (S * BT, 2), torch.float32)
 
     # ---- one denoiser evaluation ------------------------------------------------------------------------
     def denoise(self, x_in: torch.Tensor, t_dev: torch.Tensor) -> torch.Tensor:
@@ -224,18 +245,44 @@ class DenoiserEngine:
             lib.gemm(x_in, w["le_w"], x[s * BT:(s + 1) * BT], bias=w["le_b"],
                      act=lib.ACT_MISH if P.latent_mish else lib.ACT_NONE, residual=self.addend[s0 + s])
         scale = 1.0 / math.sqrt(P.dh)
+        rows = r1 - r0
+        if not self.fold:
+            for l in range(P.layers):
+                L = w[l]
+                lib.gemm(x, L["qkv_w"], qkv, bias=L["qkv_b"])
+                lib.self_attention(qkv[:, 0:], qkv[:, d:], qkv[:, 2 * d:], att, n * B, T, T, P.heads, P.dh, scale,
+                                   slopes=w["slopes"], period=P.period)
+                lib.gemm(att, L["o_w"], proj, bias=L["o_b"], residual=x)
+                lib.layernorm(proj, x, g1=L["n1_w"], b1=L["n1_b"], r2=self.cross[l], vec2=L["time_cross"],
+                              vec_index_dev=t_dev, g2=L["n2_w"], b2=L["n2_b"])
+                lib.gemm(x, L["f1_w"], ffn, bias=L["f1_b"], act=lib.ACT_RELU)
+                lib.gemm(ffn, L["f2_w"], proj, bias=L["f2_b"], residual=x)
+                lib.layernorm(proj, x, g1=L["n3_w"], b1=L["n3_b"])
+            lib.gemm(x, w["ld_w"], self.x0.view(self.passes * BT, d)[r0:r1], bias=w["ld_b"])
+            return
+        # ---- norm3 folded into the neighbouring GEMMs: `proj` carries u = x + FFN(x) between layers, `mr` its (mean, rstd) ----
+        parts, mr = self.ln_parts[r0:r1], self.ln_mr[r0:r1]
         for l in range(P.layers):
             L = w[l]
-            lib.gemm(x, L["qkv_w"], qkv, bias=L["qkv_b"])
+            if l == 0:
+                lib.gemm(x, L["qkv_w"], qkv, bias=L["qkv_b"])
+            else:
+                lib.gemm(proj, L["qkv_wf"], qkv, bias=L["qkv_bf"], a_ln=mr, w_colsum=L["qkv_cs"])
             lib.self_attention(qkv[:, 0:], qkv[:, d:], qkv[:, 2 * d:], att, n * B, T, T, P.heads, P.dh, scale,
                                slopes=w["slopes"], period=P.period)
-            lib.gemm(att, L["o_w"], proj, bias=L["o_b"], residual=x)
-            lib.layernorm(proj, x, g1=L["n1_w"], b1=L["n1_b"], r2=self.cross[l], vec2=L["time_cross"],
+            if l == 0:
+                lib.gemm(att, L["o_w"], proj, bias=L["o_b"], residual=x)
+                u1 = proj
+            else:  # residual = LN3(u) of the previous layer, rebuilt in the epilogue from `proj`
+                lib.gemm(att, L["o_w"], x, bias=L["o_b"], residual=proj, res_ln=mr, res_gamma=w[l - 1]["n3_w"],
+                         res_beta=w[l - 1]["n3_b"])
+                u1 = x
+            lib.layernorm(u1, x, g1=L["n1_w"], b1=L["n1_b"], r2=self.cross[l], vec2=L["time_cross"],
                           vec_index_dev=t_dev, g2=L["n2_w"], b2=L["n2_b"])
             lib.gemm(x, L["f1_w"], ffn, bias=L["f1_b"], act=lib.ACT_RELU)
-            lib.gemm(ffn, L["f2_w"], proj, bias=L["f2_b"], residual=x)
-            lib.layernorm(proj, x, g1=L["n3_w"], b1=L["n3_b"])
-        lib.gemm(x, w["ld_w"], self.x0.view(self.passes * BT, d)[r0:r1], bias=w["ld_b"])
+            lib.gemm(ffn, L["f2_w"], proj, bias=L["f2_b"], residual=x, stats_out=parts)
+            lib.ln_stats_finalize(parts, rows, d // 64, d, mr)
+        lib.gemm(proj, w["ld_wf"], self.x0.view(self.passes * BT, d)[r0:r1], bias=w["ld_bf"], a_ln=mr, w_colsum=w["ld_cs"])
 
     def kernels_per_step(self) -> int:
         return (self.passes + 2 * (7 * self.P.layers + 1)) if (self.passes == 2 and self.lanes == 2) else (self.passes + 7 * self.P.layers + 1)

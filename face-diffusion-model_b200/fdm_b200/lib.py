@@ -25,7 +25,8 @@ class GemmArgs(C.Structure):
     _fields_ = [("A", _vp), ("lda", _i64), ("a_rows", _i64), ("W", _vp), ("ldw", _i64), ("bias", _vp),
                 ("residual", _vp), ("ldr", _i64), ("res_dtype", _i32), ("out_dtype", _i32), ("C", _vp),
                 ("ldc", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("act", _i32), ("taps", _i32),
-                ("tap_k", _i64), ("tap_row_shift", _i64)]
+                ("tap_k", _i64), ("tap_row_shift", _i64), ("a_ln", _vp), ("w_colsum", _vp), ("res_ln", _vp),
+                ("res_gamma", _vp), ("res_beta", _vp), ("stats_out", _vp)]
 
 
 class NormArgs(C.Structure):
@@ -60,6 +61,7 @@ EXPORTS = {
     "fdm_abi_version": (C.c_int, []),
     "fdm_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "fdm_ln_stats_finalize": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _vp, _vp]),
     "fdm_layernorm": (C.c_int, [C.POINTER(NormArgs), _vp]),
     "fdm_leaky_instnorm": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _i32, _vp]),
     "fdm_self_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
@@ -150,7 +152,10 @@ def _launched(n: int = 1) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, *, M: Optional[int] = None,
          lda: Optional[int] = None, a_rows: Optional[int] = None, taps: int = 1, tap_k: int = 0,
-         tap_row_shift: int = 0, K: Optional[int] = None) -> torch.Tensor:
+         tap_row_shift: int = 0, K: Optional[int] = None, a_ln: Optional[torch.Tensor] = None,
+         w_colsum: Optional[torch.Tensor] = None, res_ln: Optional[torch.Tensor] = None,
+         res_gamma: Optional[torch.Tensor] = None, res_beta: Optional[torch.Tensor] = None,
+         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual; bf16 operands -> tcgen05, f32 -> FFMA.
 
     `a` may be any tensor whose storage holds the rows (lda/a_rows/M override the 2-D view for implicit
@@ -175,9 +180,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     g.ldc = out.stride(0)
     g.N, g.K = N, Kk
     g.act, g.taps, g.tap_k, g.tap_row_shift = act, taps, tap_k, tap_row_shift
+    # LayerNorm folding (bf16 path; see fdm_gemm_args)
+    g.a_ln, g.w_colsum, g.res_ln = _ptr(a_ln), _ptr(w_colsum), _ptr(res_ln)
+    g.res_gamma, g.res_beta, g.stats_out = _ptr(res_gamma), _ptr(res_beta), _ptr(stats_out)
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.numel() >= g.M * (N // 64) * 2
     assert out.shape[0] >= g.M and out.shape[1] == N
     fn = lib.fdm_gemm_bf16 if a.dtype == torch.bfloat16 else lib.fdm_gemm_f32
     _check(fn(C.byref(g), _stream()))
+    _launched()
+    return out
+
+
+def ln_stats_finalize(partials: torch.Tensor, M: int, parts: int, d: int, out: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per row [M, 2] from the [M, parts, 2] partial statistics written by gemm(..., stats_out=...)."""
+    assert partials.dtype == torch.float32 and out.dtype == torch.float32 and out.numel() >= 2 * M
+    _check(require_device().fdm_ln_stats_finalize(_ptr(partials), M, parts, d, eps, _ptr(out), _stream()))
     _launched()
     return out
 

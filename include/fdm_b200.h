@@ -67,12 +67,30 @@ typedef struct fdm_gemm_args {
   int32_t taps;           /* 1 = plain GEMM */
   int64_t tap_k;
   int64_t tap_row_shift;
+  /* ---- LayerNorm folding (fdm_gemm_bf16 only; every pointer NULL = plain GEMM) -------------------------------------
+   * A post-norm layer ends in y = LN(u; gamma, beta). Instead of materialising y, the GEMM that produces u also writes
+   * per-row partial statistics (stats_out), fdm_ln_stats_finalize turns them into (mean, rstd) per row, and
+   *  - a consumer y W^T is computed from u with pre-scaled weights W' = W diag(gamma):
+   *        C = rstd (u W'^T - mean * w_colsum) + bias',   w_colsum[n] = sum_k W'[n,k],  bias' = bias + W beta   (a_ln)
+   *  - a residual  "+ y"  is rebuilt element-wise from u:  (u - mean) rstd res_gamma + res_beta                 (res_ln)
+   * This removes the LayerNorm kernel between two GEMMs (one read and one write of the activation). */
+  const float* a_ln;       /* [M][2] (mean, rstd) of the rows of A, or NULL */
+  const float* w_colsum;   /* [N], required with a_ln */
+  const float* res_ln;     /* [M][2] (mean, rstd) of the rows of `residual`, or NULL (needs the bf16-in / bf16-out TMA path) */
+  const float* res_gamma;  /* [N] */
+  const float* res_beta;   /* [N] */
+  float* stats_out;        /* [M][N/64][2]: per 64-column group, sum and sum of squares of the fp32 OUTPUT row values;
+                              needs the bf16 residual TMA path and N % 64 == 0, or NULL */
 } fdm_gemm_args;
 
 /* TMA-fed tcgen05/TMEM GEMM, bf16 operands, fp32 accumulation. */
 int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream);
 /* fp32 FFMA GEMM (deterministic k order) — the "fp32 mode" used for the 1e-4 parity runs. */
 int fdm_gemm_f32(const fdm_gemm_args* args, void* stream);
+/* (mean, rstd) per row from the partial statistics a GEMM wrote through stats_out: partials [M][parts][2] (sum, sum
+ * of squares per column group), d = number of columns they cover; mean_rstd [M][2]. Deterministic (fixed order). */
+int fdm_ln_stats_finalize(const float* partials, int64_t M, int64_t parts, int64_t d, float eps, float* mean_rstd,
+                          void* stream);
 
 /* ---- normalisation ------------------------------------------------------- *
  * Row LayerNorm with fused residual adds; replaces norm1/2/3 of nn.TransformerDecoderLayer

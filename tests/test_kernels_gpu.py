@@ -118,6 +118,60 @@ def test_gemm_implicit_conv(cuda_dev, dtype):
     assert _rel(got2, ref2) < (2e-5 if dtype == torch.float32 else 1e-4)
 
 
+@pytest.mark.parametrize("M,d,big", [(600, 1024, False), (333, 512, False), (25344, 1024, True)])
+def test_gemm_layernorm_folding(cuda_dev, M, d, big):
+    """LayerNorm folded into the neighbouring GEMMs (fdm_gemm_args a_ln / res_ln / stats_out + fdm_ln_stats_finalize):
+    producer statistics, the consumer computed from un-normalised rows with pre-scaled weights, and the residual
+    rebuilt element-wise, each against the plain fp32 statement LN(u) on the same bf16 operands."""
+    from fdm_b200 import lib
+    g = torch.Generator(device="cpu").manual_seed(M + d)
+    dev = cuda_dev
+    K0, N2 = 2 * d, 3 * d
+    A0 = (torch.randn(M, K0, generator=g) * 0.5).to(dev).bfloat16()
+    W0 = (torch.randn(d, K0, generator=g) / K0 ** 0.5).to(dev).bfloat16()
+    b0 = (0.1 * torch.randn(d, generator=g)).to(dev)
+    R0 = (torch.randn(M, d, generator=g) + 0.3).to(dev).bfloat16()  # non-zero row mean
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(d, generator=g)).to(dev)
+    # producer: u = A0 W0^T + b0 + R0 (bf16) with per-row partial statistics
+    parts = d // 64
+    u = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+    stats = torch.zeros(M, parts, 2, device=dev)
+    lib.gemm(A0, W0, u, bias=b0, residual=R0, stats_out=stats)
+    u32 = A0.float() @ W0.float().t() + b0 + R0.float()
+    assert (u.float() - u32).abs().max().item() < 0.05
+    ref_parts = torch.stack([u32.view(M, parts, 64).sum(-1), (u32 ** 2).view(M, parts, 64).sum(-1)], dim=-1)
+    assert (stats - ref_parts).abs().max().item() < 2e-3 * ref_parts.abs().max().item()
+    mr = torch.empty(M, 2, device=dev)
+    lib.ln_stats_finalize(stats, M, parts, d, mr)
+    mean, var = u32.mean(-1), u32.var(-1, unbiased=False)
+    assert (mr[:, 0] - mean).abs().max().item() < 1e-4
+    assert ((mr[:, 1] - (var + 1e-5).rsqrt()) / mr[:, 1]).abs().max().item() < 1e-3
+    y = torch.nn.functional.layer_norm(u.float(), (d,), gamma, beta, 1e-5)  # what the LayerNorm kernel would produce (fp32)
+    # consumer: y W2^T + b2 from u with W' = W2 diag(gamma)
+    W2 = (torch.randn(N2, d, generator=g) / d ** 0.5).to(dev)
+    b2 = (0.1 * torch.randn(N2, generator=g)).to(dev)
+    Wp = (W2 * gamma[None]).bfloat16()
+    colsum = Wp.float().sum(-1).contiguous()
+    bias_p = (b2 + W2 @ beta).contiguous()
+    out = torch.empty(M, N2, device=dev, dtype=torch.bfloat16)
+    lib.gemm(u, Wp, out, bias=bias_p, a_ln=mr, w_colsum=colsum)
+    ref = y @ W2.t() + b2
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-2, rel
+    # residual: A3 W3^T + b3 + y with y rebuilt from u inside the epilogue
+    A3 = (torch.randn(M, d, generator=g)).to(dev).bfloat16()
+    W3 = (torch.randn(d, d, generator=g) / d ** 0.5).to(dev).bfloat16()
+    out3 = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+    stats3 = torch.zeros(M, parts, 2, device=dev)
+    lib.gemm(A3, W3, out3, bias=b0, residual=u, res_ln=mr, res_gamma=gamma, res_beta=beta, stats_out=stats3)
+    ref3 = A3.float() @ W3.float().t() + b0 + y
+    assert ((out3.float() - ref3).norm() / ref3.norm()).item() < 5e-3
+    ref_parts3 = torch.stack([ref3.view(M, parts, 64).sum(-1), (ref3 ** 2).view(M, parts, 64).sum(-1)], dim=-1)
+    assert (stats3 - ref_parts3).abs().max().item() < 5e-3 * ref_parts3.abs().max().item()
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("M,N,K", [(198, 1024, 1024), (77, 130, 50), (512, 15069, 64), (300, 64, 2048)])
 def test_gemm_f32(cuda_dev, M, N, K):
     from fdm_b200 import lib
