@@ -540,8 +540,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   f.y = fmaf((f.y - r_mean) * r_rstd, gm.y, bt.y);
                 }
                 const float o0 = v[8 * j + 2 * e] + f.x, o1 = v[8 * j + 2 * e + 1] + f.y;
-                st_s += o0 + o1;
-                st_q = fmaf(o0, o0, fmaf(o1, o1, st_q));
+                if (ep.stats_out) {  // (warp-uniform; the plain path must not pay for the statistics)
+                  st_s += o0 + o1;
+                  st_q = fmaf(o0, o0, fmaf(o1, o1, st_q));
+                }
                 oo[e] = pack2(o0, o1);
               }
               st_shared_v4(addr, oo[0], oo[1], oo[2], oo[3]);
