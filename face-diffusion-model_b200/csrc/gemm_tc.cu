@@ -265,11 +265,14 @@ __device__ __forceinline__ void act_inplace(float (&v)[32], int act) {
 }
 
 // bias + activation + residual for 32 consecutive columns [col0, col0+32) of output row `row`
+// FOLD = false compiles the LayerNorm-folding branches out: the plain kernels are instruction-for-instruction what they
+// were before the feature (launch-bound problems such as MEAD's d = 512 GEMMs lost 10 % to the extra uniform branches).
+template <bool FOLD>
 __device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep, int64_t row, bool row_ok, int col0, int N,
                                               float a_mean = 0.f, float a_rstd = 1.f) {
   const int ncols = min(32, N - col0);
   const bool full = ncols == 32;
-  if (ep.a_ln) {  // A held un-normalised rows: C = rstd (acc - mean * colsum(W')) (+ bias' below)
+  if (FOLD && ep.a_ln) {  // A held un-normalised rows: C = rstd (acc - mean * colsum(W')) (+ bias' below)
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < ncols) v[j] = a_rstd * fmaf(-a_mean, __ldg(ep.w_colsum + col0 + j), v[j]);
@@ -348,7 +351,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BLOCK_N, int CG>
+template <int BLOCK_N, int CG, bool FOLD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
@@ -523,7 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int64_t row = static_cast<int64_t>(row_w) + lane;
         const bool row_ok = row < M;
         float r_mean = 0.f, r_rstd = 1.f;
-        if (ep.res_ln && row_ok) {
+        if (FOLD && ep.res_ln && row_ok) {
           const float2 mr = __ldg(reinterpret_cast<const float2*>(ep.res_ln) + row);
           r_mean = mr.x;
           r_rstd = mr.y;
@@ -547,7 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             {  // bias + activation (no residual here)
               Epilogue e2 = ep;
               e2.residual = nullptr;
-              epilogue_math(v, e2, 0, false, col0 + half * 32, N);
+              epilogue_math<false>(v, e2, 0, false, col0 + half * 32, N);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -559,7 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
-                if (ep.res_ln) {  // the residual tile holds un-normalised rows: rebuild LN(u) element-wise
+                if (FOLD && ep.res_ln) {  // the residual tile holds un-normalised rows: rebuild LN(u) element-wise
                   const int col = col0 + half * 32 + 8 * j + 2 * e;
                   const float2 gm = __ldg(reinterpret_cast<const float2*>(ep.res_gamma + col));
                   const float2 bt = __ldg(reinterpret_cast<const float2*>(ep.res_beta + col));
@@ -567,7 +570,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   f.y = fmaf((f.y - r_mean) * r_rstd, gm.y, bt.y);
                 }
                 const float o0 = v[8 * j + 2 * e] + f.x, o1 = v[8 * j + 2 * e + 1] + f.y;
-                if (ep.stats_out) {  // (warp-uniform; the plain path must not pay for the statistics)
+                if (FOLD && ep.stats_out) {  // (warp-uniform; the plain path must not pay for the statistics)
                   st_s += o0 + o1;
                   st_q = fmaf(o0, o0, fmaf(o1, o1, st_q));
                 }
@@ -576,7 +579,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               st_shared_v4(addr, oo[0], oo[1], oo[2], oo[3]);
             }
           }
-          if (ep.stats_out && row_ok)
+          if (FOLD && ep.stats_out && row_ok)
             *reinterpret_cast<float2*>(ep.stats_out + (row * ep.stats_parts + (col0 >> 6)) * 2) = make_float2(st_s, st_q);
           fence_async_smem();
           __syncwarp();
@@ -601,7 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t row = static_cast<int64_t>(row_w) + lane;
       const bool row_ok = row < M;
       float a_mean = 0.f, a_rstd = 1.f;
-      if (ep.a_ln && row_ok) {
+      if (FOLD && ep.a_ln && row_ok) {
         const float2 mr = __ldg(reinterpret_cast<const float2*>(ep.a_ln) + row);
         a_mean = mr.x;
         a_rstd = mr.y;
@@ -621,7 +624,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_math(v, ep, row, row_ok, col0, N, a_mean, a_rstd);
+          epilogue_math<FOLD>(v, ep, row, row_ok, col0, N, a_mean, a_rstd);
           if (out_bf16) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -641,7 +644,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_math(v, ep, row, row_ok, col0 + 32, N, a_mean, a_rstd);
+          epilogue_math<FOLD>(v, ep, row, row_ok, col0 + 32, N, a_mean, a_rstd);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_shared_v4(sbuf + stage_off(lane, 4 + j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
@@ -735,12 +738,12 @@ int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int BLOCK_N, int CG = 1>
-int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
+template <int BLOCK_N, int CG, bool FOLD>
+int launch_impl(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int taps = a.taps > 1 ? a.taps : 1;
@@ -766,10 +769,16 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   static const int sm_limit = [] { const char* e = getenv("FDM_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();  // experiments only
   const int64_t slots = (sm_limit > 0 ? sm_limit : fdm_sm_count()) / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
   const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
-  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
+  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
                                 tm_c, tm_r, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
                                 taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles));
   return 0;
+}
+
+template <int BLOCK_N, int CG = 1>
+int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
+  if (ep.a_ln || ep.res_ln || ep.stats_out) return launch_impl<BLOCK_N, CG, true>(a, ep, stream);
+  return launch_impl<BLOCK_N, CG, false>(a, ep, stream);
 }
 
 }  // namespace

@@ -1,5 +1,6 @@
 import os, sys, math, torch
-sys.path[:0] = ['/root/repo', '/root/repo/face-diffusion-model_b200']
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'face-diffusion-model_b200')]
 from fdm_b200 import lib
 lib.require_device()
 dev = torch.device('cuda:0')
