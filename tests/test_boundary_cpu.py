@@ -77,3 +77,41 @@ def test_no_cpu_fallback():
         lib.require_device()
     with pytest.raises((lib.FdmError, AssertionError)):
         lib.gemm(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 4))
+
+
+def test_ctypes_structs_mirror_the_header():
+    """The ctypes argument structs of fdm_b200/lib.py must list the fields of include/fdm_b200.h's structs in the same
+    order with matching widths, and sizeof must agree with what the compiler laid out (a tiny C program prints it)."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    from fdm_b200 import lib
+    hdr_path = os.path.join(ROOT, "include", "fdm_b200.h")
+    hdr = re.sub(r"/\*.*?\*/", "", open(hdr_path).read(), flags=re.S)
+    pairs = {"fdm_gemm_args": lib.GemmArgs, "fdm_norm_args": lib.NormArgs, "fdm_attn_args": lib.AttnArgs,
+             "fdm_ddpm_args": lib.DdpmArgs, "fdm_ddim_args": lib.DdimArgs}
+    width = {"int64_t": 8, "uint64_t": 8, "int32_t": 4, "float": 4}
+    for cname, cls in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.*)", decl)
+            ctype, star, names = m.group(2), m.group(3), m.group(4)
+            for nm in names.split(","):
+                nm = nm.strip()
+                ptr = bool(star) or nm.startswith("*")
+                fields.append((nm.lstrip("* "), 8 if ptr else width[ctype]))
+        got = [(n, C.sizeof(t)) for n, t in cls._fields_]
+        assert got == fields, (cname, [a for a, b in zip(got, fields) if a != b][:3], len(got), len(fields))
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "s.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu %%zu %%zu\\n", sizeof(fdm_gemm_args), '
+                    'sizeof(fdm_norm_args), sizeof(fdm_attn_args), sizeof(fdm_ddpm_args), sizeof(fdm_ddim_args));return 0;}\n' % hdr_path)
+        exe = os.path.join(td, "s")
+        subprocess.check_call(["gcc", "-o", exe, src])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(c) for c in pairs.values()], sizes
