@@ -124,3 +124,18 @@ def test_oracle_vq_encode(preset):
     got = R.vq_encode(sd, preset, x, emo)
     assert got.shape == want.shape
     assert (got - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
+
+
+def test_audio_frontend_formula_is_the_processors():
+    """Pins the statement the device front-end is tested against (tests/test_parity_gpu.py::test_audio_frontend_...):
+    (x - mean) / sqrt(var + 1e-7) is what the installed Wav2Vec2 feature extractor - the arithmetic behind the
+    Wav2Vec2Processor call of demo/demo_3d_mead.py:85-89 - produces for a mono clip."""
+    import numpy as np
+    from transformers import Wav2Vec2FeatureExtractor
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(48000) * 0.05 + 0.01).astype(np.float32)
+    fe = Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
+                                  return_attention_mask=False)  # wav2vec2-base-960h's preprocessor_config.json
+    got = np.squeeze(fe(x, sampling_rate=16000).input_values)
+    want = (x - x.mean()) / np.sqrt(x.var() + 1e-7)
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-5
