@@ -180,7 +180,10 @@ __device__ __forceinline__ void ln2rows(float (&v)[2][EPL], int lane, float eps,
   }
 }
 
-template <typename T, int EPL>
+// MODE 0: every option decided at run time. MODE 1: plain LayerNorm (g1 only). MODE 2: the denoiser's fused pair
+// LN1 -> + cross-attention cache (r2) + time row (vec2) -> LN2. The specialisations drop the uniform branches and the
+// code behind them (same lesson as the GEMM epilogue: they cost registers and issue slots even when not taken).
+template <typename T, int EPL, int MODE>
 __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args a) {
   constexpr int CE = Chunk<T>::CE;
   constexpr int NCH = EPL / CE;
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args
 #pragma unroll
       for (int e = 0; e < CE; ++e) v[r][i * CE + e] = t[e];
     }
-    if (a.r1) {
+    if (MODE == 0 && a.r1) {
       const T* rp = reinterpret_cast<const T*>(a.r1) + rows[r] * a.ldr1;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
@@ -213,13 +216,13 @@ __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args
       }
     }
   }
-  if (a.g1) ln2rows<EPL, CE>(v, lane, a.eps, a.g1, a.b1);
-  if (a.act1 == FDM_ACT_GELU_ERF) {
+  if (MODE != 0 || a.g1) ln2rows<EPL, CE>(v, lane, a.eps, a.g1, a.b1);
+  if (MODE == 0 && a.act1 == FDM_ACT_GELU_ERF) {
 #pragma unroll
     for (int e = 0; e < EPL; ++e) { v[0][e] = act_gelu_erf(v[0][e]); v[1][e] = act_gelu_erf(v[1][e]); }
   }
-  if (a.g2) {
-    if (a.r2) {
+  if (MODE == 2 || (MODE == 0 && a.g2)) {
+    if (MODE == 2 || a.r2) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int64_t rr = a.r2_rows > 0 ? rows[r] % a.r2_rows : rows[r];
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args
         }
       }
     }
-    if (a.vec2) {
+    if (MODE == 2 || a.vec2) {
       const float* vec = a.vec2 + static_cast<int64_t>(*a.vec_index_dev) * (EPL * 32);
 #pragma unroll
       for (int i = 0; i < NCH; ++i)
@@ -261,11 +264,19 @@ __global__ void __launch_bounds__(128) layernorm_fast_kernel(const fdm_norm_args
   }
 }
 
+template <typename T, int EPL>
+bool launch_fast_ln(const fdm_norm_args& a, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, 8));
+  const bool plain = a.g1 && !a.r1 && a.act1 == FDM_ACT_NONE && !a.g2;
+  const bool pair = a.g1 && !a.r1 && a.act1 == FDM_ACT_NONE && a.g2 && a.r2 && a.vec2;
+  if (plain) return fdm_launch_pdl(layernorm_fast_kernel<T, EPL, 1>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+  if (pair) return fdm_launch_pdl(layernorm_fast_kernel<T, EPL, 2>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+  return fdm_launch_pdl(layernorm_fast_kernel<T, EPL, 0>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+}
 template <typename T>
 bool try_fast_ln(const fdm_norm_args& a, cudaStream_t s) {
-  const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, 8));
-  if (a.d == 1024) return fdm_launch_pdl(layernorm_fast_kernel<T, 32>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
-  if (a.d == 512) return fdm_launch_pdl(layernorm_fast_kernel<T, 16>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+  if (a.d == 1024) return launch_fast_ln<T, 32>(a, s);
+  if (a.d == 512) return launch_fast_ln<T, 16>(a, s);
   return false;
 }
 
