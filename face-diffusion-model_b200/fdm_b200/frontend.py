@@ -31,3 +31,53 @@ def vertex_metrics(pred: torch.Tensor, gt: torch.Tensor, lip_idx: Optional[torch
         if idx is not None:
             out[name] = float(lib.vertex_error(p, g, idx.to(p.device, torch.int64).contiguous(), mode).mean())
     return out
+
+
+class VertexWriter:
+    """`.npy` writer of the sample scripts (np.save of a (1, T, V*3) fp32 array per clip,
+    samples/sample_diffusion_mead.py:86), off the critical path: the vertices are copied device -> pinned host on a
+    side stream (overlapping the all-gather / the next job) and written by a worker thread."""
+
+    def __init__(self):
+        import queue
+        import threading
+        self._q = queue.Queue()
+        self._stream = None
+        self._err = None
+        self._t = threading.Thread(target=self._work, daemon=True)
+        self._t.start()
+
+    def _work(self):
+        import numpy as np
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            host, ev, paths = item
+            try:
+                ev.synchronize()
+                arr = host.numpy()
+                for i, path in enumerate(paths):
+                    np.save(path, arr[i:i + 1])
+            except Exception as e:  # surfaced by close()
+                self._err = e
+
+    def submit(self, verts: torch.Tensor, paths) -> None:
+        """verts (B, T, V*3) fp32 on the GPU; paths: B file names. Returns immediately."""
+        assert verts.is_cuda and verts.dim() == 3 and len(paths) == verts.shape[0]
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=verts.device)
+        host = torch.empty(verts.shape, dtype=torch.float32, pin_memory=True)
+        self._stream.wait_stream(torch.cuda.current_stream(verts.device))
+        with torch.cuda.stream(self._stream):
+            host.copy_(verts.detach().float(), non_blocking=True)
+            verts.record_stream(self._stream)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        self._q.put((host, ev, list(paths)))
+
+    def close(self) -> None:
+        self._q.put(None)
+        self._t.join()
+        if self._err is not None:
+            raise self._err

@@ -256,6 +256,18 @@ def test_audio_frontend_and_vertex_metrics(cuda_dev):
             "eme": d2[:, face[::2]].mean(1).mean()}
     for k, v in want.items():
         assert abs(got[k] - v) <= 1e-5 * abs(v), (k, got[k], v)
+    # .npy writer of the sample scripts (np.save of (1, T, V*3) per clip), asynchronous
+    import tempfile
+    from fdm_b200.frontend import VertexWriter
+    verts = torch.randn(3, 20, 15069, generator=g).to(cuda_dev)
+    with tempfile.TemporaryDirectory() as td:
+        paths = [os.path.join(td, f"clip{i}.npy") for i in range(3)]
+        w = VertexWriter()
+        w.submit(verts, paths)
+        w.close()
+        for i, pth in enumerate(paths):
+            a = np.load(pth)
+            assert a.shape == (1, 20, 15069) and np.array_equal(a[0], verts[i].cpu().numpy())
 
 
 def test_cached_step_graphs_are_reused_and_keyed(cuda_dev):
