@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Timeline of the tensor-core VQ kernel's pipeline roles for CTA 0 (needs a library built with -DVQ_TRACE, see
-vq_tc.cu; pass its path in FDM_B200_LIB). Prints per-tile clock64 stamps relative to the first one."""
+vq_tc.cu: `make -C face-diffusion-model_b200/csrc trace` writes tools/_trace/libfdm_trace.so; run with
+FDM_B200_LIB=$PWD/tools/_trace/libfdm_trace.so). Prints per-tile clock64 stamps relative to the first one."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "face-diffusion-model_b200")]
