@@ -59,6 +59,7 @@ def build_models(preset, device, precision):
     import warnings
     warnings.simplefilter("ignore")
     torch.manual_seed(0)
+    os.environ["FDM_B200_RANDOM_AUDIO_ENCODER"] = "1"  # synthetic benchmark: no checkpoint, architecture with random weights
     if preset == "vocaset":
         from models.fdm_vocaset import FDM
         from models.vq_vae_vocaset import VQAutoEncoder

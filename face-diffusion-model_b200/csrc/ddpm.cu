@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, c
   const float c1 = a.c1[t], c2 = a.c2[t], sg = a.sigma[t];
   const bool add_noise = t > 0;
   const uint32_t clip = static_cast<uint32_t>(a.clip_index0 + b);
+  const uint64_t seed = a.seed_dev ? *a.seed_dev : a.seed;  // device-resident seed: one captured graph, a fresh seed per call
   const int64_t base = b * e4_per_clip;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const fdm_ddpm_args a, c
         za = reinterpret_cast<const float4*>(a.noise)[i0];
         zb = reinterpret_cast<const float4*>(a.noise)[i1];
       } else {
-        za = philox_normal4(a.seed, clip, static_cast<uint32_t>(t), static_cast<uint64_t>(e0));
-        if (two) zb = philox_normal4(a.seed, clip, static_cast<uint32_t>(t), static_cast<uint64_t>(e1));
+        za = philox_normal4(seed, clip, static_cast<uint32_t>(t), static_cast<uint64_t>(e0));
+        if (two) zb = philox_normal4(seed, clip, static_cast<uint32_t>(t), static_cast<uint64_t>(e1));
       }
     }
     ddpm_store(a, i0, ddpm_update(a, xa, ua, ta, c1, c2), za, sg, add_noise);

@@ -354,8 +354,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int BLOCK_N, int CG, bool FOLD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep, const int M, const int N, const int num_k_blocks, const int kb_per_tap,
-               const int tap_row_shift, const int m_tiles, const int n_tiles) {
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+               const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo, const Epilogue ep,
+               const int M, const int N, const int num_k_blocks, const int kb_per_tap, const int tap_row_shift, const int m_tiles,
+               const int n_tiles, const int kb_per_seg) {
+  // num_k_blocks = segments x kb_per_seg. One segment: the plain bf16 GEMM. Three segments (split-bf16 operands): the same
+  // K range three times into the same accumulator - A_lo W_hi, A_hi W_lo, A_hi W_hi (small terms first) - only the
+  // producer's choice of tensor map differs, the MMA issuer and the epilogue see one long K loop.
   using C = Cfg<BLOCK_N, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -382,6 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b);
     if (ep.tma_c) tma_prefetch_desc(&tmap_c);
     if (ep.tma_r) tma_prefetch_desc(&tmap_r);
+    if (kb_per_seg != num_k_blocks) { tma_prefetch_desc(&tmap_a_lo); tma_prefetch_desc(&tmap_b_lo); }
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), CG);  // CG = 2: leader's expect_tx arrival + the peer's remote arrival
@@ -417,18 +423,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const int tap = kb / kb_per_tap;
-          const int kc = kb - tap * kb_per_tap;
+          const int seg = kb / kb_per_seg;       // 0 for a plain GEMM
+          const int ks = kb - seg * kb_per_seg;  // k-block inside the segment
+          const int tap = ks / kb_per_tap;
+          const int kc = ks - tap * kb_per_tap;
+          const CUtensorMap* ma = (kb_per_seg != num_k_blocks && seg == 0) ? &tmap_a_lo : &tmap_a;
+          const CUtensorMap* mb = seg == 1 ? &tmap_b_lo : &tmap_b;
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           if (CG == 1) {
             mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
-            tma_load_2d(sa + C::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+            tma_load_2d(sa, ma, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
+            tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), ks * BLOCK_K, b_row);
           } else {
             // both CTAs' bytes complete on the leader's barrier; the leader posts the whole transaction count
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-            tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
-            tma_load_2d_2sm(sa + C::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, b_row);
+            tma_load_2d_2sm(sa, ma, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
+            tma_load_2d_2sm(sa + C::A_BYTES, mb, full_bar(stage), ks * BLOCK_K, b_row);
             if (cta_rank != 0) mbar_arrive_remote(full_bar(stage), 0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -761,17 +771,24 @@ int launch_impl(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream)
   if (ep.tma_r) {
     if (int rc = make_tmap(&tm_r, a.residual, a.N, a.M, a.ldr, 32, 64, false)) return rc;
   }
+  const bool split = a.A_lo != nullptr;
+  CUtensorMap tm_a_lo = tm_a, tm_b_lo = tm_b;
+  if (split) {
+    if (int rc = make_tmap(&tm_a_lo, a.A_lo, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
+    if (int rc = make_tmap(&tm_b_lo, a.W_lo, a.K, a.N, a.ldw, BLOCK_N / CG)) return rc;
+  }
   const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M * CG));
   const int n_tiles = static_cast<int>(ceil_div64(a.N, BLOCK_N));
-  const int num_k_blocks = static_cast<int>(ceil_div64(a.K, BLOCK_K));
-  const int kb_per_tap = taps > 1 ? static_cast<int>(a.tap_k / BLOCK_K) : num_k_blocks;
+  const int kb_per_seg = static_cast<int>(ceil_div64(a.K, BLOCK_K));
+  const int num_k_blocks = kb_per_seg * (split ? 3 : 1);
+  const int kb_per_tap = taps > 1 ? static_cast<int>(a.tap_k / BLOCK_K) : kb_per_seg;
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
   static const int sm_limit = [] { const char* e = getenv("FDM_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();  // experiments only
   const int64_t slots = (sm_limit > 0 ? sm_limit : fdm_sm_count()) / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
   const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
   FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
-                                tm_c, tm_r, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks, kb_per_tap,
-                                taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles));
+                                tm_c, tm_r, tm_a_lo, tm_b_lo, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks,
+                                kb_per_tap, taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles, kb_per_seg));
   return 0;
 }
 
@@ -797,6 +814,8 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
                   "fdm_gemm_bf16: implicit conv needs K == taps*tap_k and tap_k %% 64 == 0");
   }
   FDM_CHECK_ARG(a.out_dtype == FDM_F32 || a.out_dtype == FDM_BF16, "fdm_gemm_bf16: bad out_dtype");
+  FDM_CHECK_ARG((a.A_lo == nullptr) == (a.W_lo == nullptr), "fdm_gemm_bf16: split-bf16 operands need both A_lo and W_lo");
+  FDM_CHECK_ARG(!a.A_lo || (aligned16(a.A_lo) && aligned16(a.W_lo)), "fdm_gemm_bf16: A_lo and W_lo must be 16-byte aligned");
   Epilogue ep;
   ep.bias = a.bias;
   ep.residual = a.residual;

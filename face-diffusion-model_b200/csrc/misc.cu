@@ -9,6 +9,29 @@ __global__ void __launch_bounds__(256) cast_kernel(const void* src, int sd, void
     st_from_float(dst, dd, i, ld_as_float(src, sd, i));
 }
 
+// x = hi + lo + r, |r| <= 2^-17 |x|: operand pair of the split-bf16 GEMM. 4 elements per thread (16-byte load, two 8-byte stores).
+__global__ void __launch_bounds__(256) split_bf16x2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, int64_t n) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&h0); uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ul.x = *reinterpret_cast<const uint32_t*>(&l0); ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+    reinterpret_cast<uint2*>(hi)[i] = uh;
+    reinterpret_cast<uint2*>(lo)[i] = ul;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // tail
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const __nv_bfloat16 h = __float2bfloat16_rn(src[i]);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(h));
+  }
+}
+
 __global__ void __launch_bounds__(256) transpose_kernel(const float* src, void* dst, int dd, int C, int L) {
   __shared__ float tile[32][33];
   const int64_t b = blockIdx.z;
@@ -172,6 +195,18 @@ extern "C" int fdm_cast(const void* src, int32_t src_dtype, void* dst, int32_t d
   FDM_CHECK_ARG(src && dst && n >= 0, "fdm_cast: bad arguments");
   if (n == 0) return 0;
   cast_kernel<<<grid1d(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_dtype, dst, dst_dtype, n);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, void* stream) {
+  FDM_CHECK_ARG(src && hi && lo && n >= 0, "fdm_split_bf16x2: bad arguments");
+  FDM_CHECK_ARG(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(hi) % 8 == 0 &&
+                    reinterpret_cast<uintptr_t>(lo) % 8 == 0,
+                "fdm_split_bf16x2: src must be 16-byte, hi / lo 8-byte aligned");
+  if (n == 0) return 0;
+  split_bf16x2_kernel<<<grid1d((n + 3) / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n);
   FDM_CHECK_LAUNCH();
   return 0;
 }

@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(THREADS) vq_kernel(const float* __restrict__ z
         const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
         if (od < best || (od == best && oi < bidx)) { best = od; bidx = oi; }
       }
+      // NaN / Inf row: no distance compares below +inf (the oracle's strict '<' from +inf keeps index 0; vq_tc.cu agrees)
+      if (bidx == 0x7fffffff || !(best < INFINITY)) bidx = 0;
       if (lane == 0) {
         widx[r] = bidx;
         if (r < nrows && indices) indices[b * L + l0 + r] = bidx;

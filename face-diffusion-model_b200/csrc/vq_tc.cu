@@ -26,7 +26,7 @@
 //     pipe, 3 per code) count the codes inside the window of the running maximum and accumulate their index:
 //     ind_j = sat((a_j - thr) 2^60) in {0, 1}, S = sum ind_j, J = sum ind_j j; S == 1 means "decided, index J".
 //     (Tracking (max, second max, index) with min/max/select was ALU-pipe-bound; two sweeps were TMEM-bound.)
-// Inputs containing +-Inf are outside this path's contract (use FDM_VQ_FFMA); NaNs behave like the oracle.
+// Rows containing +-Inf / NaN (|z|^2 not finite) always take the exact pass and come out as code 0, like the oracle.
 // Pipeline of one persistent CTA (448 threads, 1 CTA / SM, contiguous range of 128-row tiles):
 //   warp 8      cp.async.bulk (1-D TMA) of fp32 z quarter-tiles (32 rows = 8 KB) into a 9-deep ring (72 KB in flight)
 //   warps 10-13 fp32 -> (hi, lo) bf16 in the 128B-swizzled K-major A-operand layout, |z|^2 estimate per row
@@ -614,8 +614,11 @@ __device__ __noinline__ void role_epilogue(const Params& p, const Ctx& cx) {
       if (quad == 0) TRACE(9);
       const float Ssum = (S[0] + S[1]) + (S[2] + S[3]);
       int idx = static_cast<int>((J[0] + J[1]) + (J[2] + J[3]) + 0.5f);
-      const bool flagged = row_ok && !(Ssum == 1.0f) && window_scale > 0.f;  // (<= 0: profiling without the exact pass)
-      if (!(Ssum == 1.0f)) idx = 0;
+      // a row whose |z|^2 is +Inf / NaN has no finite distance: the oracle's strict '<' from +Inf keeps index 0. Its scores
+      // are Inf / NaN mixtures that could fake S == 1, so such rows always take the exact pass (empty candidate masks -> 0).
+      const bool nonfinite = !(zzr < INFINITY);
+      const bool flagged = row_ok && (!(Ssum == 1.0f) || nonfinite) && window_scale > 0.f;  // (<= 0: profiling, no exact pass)
+      if (!(Ssum == 1.0f) || nonfinite) idx = 0;
       uint32_t fl = __ballot_sync(0xffffffffu, flagged);
       if (fl) {
         // ---- second look at the accumulator, only at the chunks that hold candidates of a flagged row: per-row candidate

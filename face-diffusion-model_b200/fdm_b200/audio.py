@@ -23,12 +23,13 @@ from . import lib
 
 class AudioEncoderEngine:
     def __init__(self, hf_model: torch.nn.Module, precision: str = "bf16"):
-        assert precision in ("bf16", "fp32")
+        assert precision in ("bf16", "fp32", "x3")  # "x3": fp32 activations, split-bf16 tensor-core GEMMs (see DenoiserEngine)
         self.m = hf_model
         self.cfg = hf_model.config
         self.precision = precision
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self._packed_key = None
+        self.pack_serial = 0  # bumped whenever the weights are (re)packed: caches of encoder outputs key on it
         cfg = self.cfg
         # two architecture families: hubert-large-ls960-ft ("layer" feature-encoder norm, conv bias, pre-LN "stable"
         # encoder) and wav2vec2-base-960h ("group" norm on the first conv only, no conv bias, post-LN encoder)
@@ -46,7 +47,10 @@ class AudioEncoderEngine:
         cfg, m = self.cfg, self.m
         dev = next(m.parameters()).device
         assert dev.type == "cuda", "audio encoder must live on a CUDA device (no CPU fallback)"
-        W = lambda t: t.detach().to(self.dtype).contiguous()
+        if self.precision == "x3":
+            W = lambda t: lib.split(t.detach().float().contiguous())
+        else:
+            W = lambda t: t.detach().to(self.dtype).contiguous()
         Fv = lambda t: t.detach().float().contiguous()
         w = {}
         convs = m.feature_extractor.conv_layers
@@ -71,7 +75,7 @@ class AudioEncoderEngine:
         C = cfg.hidden_size
         cg = C // G
         # the tcgen05 implicit-conv path needs 64-element taps: pad each group's input channels to a multiple of 64
-        self.cg_pad = cg if (self.dtype == torch.float32 or cg % 64 == 0) else (cg + 63) // 64 * 64
+        self.cg_pad = cg if (self.precision == "fp32" or cg % 64 == 0) else (cg + 63) // 64 * 64
         w["pos_w"] = []
         for g in range(G):
             wg = pw[g * cg:(g + 1) * cg].permute(0, 2, 1)  # [cout, k, cin]
@@ -92,6 +96,7 @@ class AudioEncoderEngine:
                 f2_w=W(lyr.feed_forward.output_dense.weight), f2_b=Fv(lyr.feed_forward.output_dense.bias)))
         w["ln_g"], w["ln_b"] = Fv(m.encoder.layer_norm.weight), Fv(m.encoder.layer_norm.bias)
         self.w, self.dev, self._packed_key = w, dev, key
+        self.pack_serial += 1
 
     def frame_counts(self, n_samples: int) -> List[int]:
         out, n = [], n_samples
@@ -101,8 +106,10 @@ class AudioEncoderEngine:
         return out
 
     @torch.no_grad()
-    def encode(self, audio: torch.Tensor) -> torch.Tensor:
-        """audio (B, L) fp32 on device -> last_hidden_state (B, N, hidden) in the compute dtype, N even."""
+    def encode(self, audio: torch.Tensor, max_frames: int = None) -> torch.Tensor:
+        """audio (B, L) fp32 on device -> last_hidden_state (B, N, hidden) in the compute dtype, N even.
+        max_frames: the reference's `frame_num` cut (models/hubert.py:97-98), applied to the conv features BEFORE the
+        feature projection and the encoder, so the attention only ever sees the kept frames."""
         self.pack()
         cfg, w, dev, dt = self.cfg, self.w, self.dev, self.dtype
         assert audio.dim() == 2 and audio.dtype == torch.float32 and audio.is_cuda
@@ -135,6 +142,8 @@ class AudioEncoderEngine:
                          K=cv["k"] * cfg.conv_dim[i - 1])
             cur = nxt
         N = lens[-1] - (lens[-1] % 2)  # models/hubert.py:95-96 / models/wav2vec.py:88-89: drop an odd last frame
+        if max_frames and N > max_frames:
+            N = int(max_frames)
         Lp = strides[-1]
         C = cfg.hidden_size
         M = B * Lp
@@ -158,6 +167,8 @@ class AudioEncoderEngine:
             xg = xpad
         x = torch.zeros(B * Tp, C, device=dev, dtype=dt)
         Mp = B * Tp - (kpos - 1)
+        if self.precision == "x3":
+            xg = lib.split(xg)  # every group's GEMM reads a column slice of the same buffer: split it once
         for g in range(G):
             lib.gemm(xg[:, g * cgp:], w["pos_w"][g], x[:, g * cg:(g + 1) * cg], bias=w["pos_b"][g], act=lib.ACT_GELU_ERF,
                      residual=xpad[pad:, g * cg:(g + 1) * cg], M=Mp, lda=G * cgp, a_rows=B * Tp, taps=kpos, tap_k=cgp, tap_row_shift=1)

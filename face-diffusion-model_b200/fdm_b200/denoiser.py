@@ -34,7 +34,10 @@ def _sin_table(n: int, d: int) -> torch.Tensor:
 
 class DenoiserEngine:
     def __init__(self, module: torch.nn.Module, preset: Preset, precision: str = "bf16"):
-        assert precision in ("bf16", "fp32")
+        # "bf16": bf16 operands and activations (throughput mode); "fp32": FFMA GEMMs, exact fp32 attention (parity mode);
+        # "x3": fp32 activations, GEMMs on the tensor cores with split-bf16 operands (A_lo W + A W_lo + A W, 2^-17 relative):
+        # the high-precision tail steps of the bf16 sampler
+        assert precision in ("bf16", "fp32", "x3")
         self.module = module
         self.P = preset
         self.precision = precision
@@ -63,7 +66,11 @@ class DenoiserEngine:
         P, d = self.P, self.P.d
         dev = next(iter(sd.values())).device
         assert dev.type == "cuda", "FDM must live on a CUDA device (no CPU fallback)"
-        W = lambda k: sd[k].detach().to(self.dtype).contiguous()
+        if self.precision == "x3":
+            Wt = lambda t: lib.split(t.detach().float().contiguous())
+        else:
+            Wt = lambda t: t.detach().to(self.dtype).contiguous()
+        W = lambda k: Wt(sd[k])
         Bv = lambda k: sd[k].detach().float().contiguous()
         w = {}
         w["ae0_w"], w["ae0_b"] = W("audio_extract.0.weight"), Bv("audio_extract.0.bias")
@@ -88,7 +95,7 @@ class DenoiserEngine:
             L["qkv_w"], L["qkv_b"] = W(p + "self_attn.in_proj_weight"), Bv(p + "self_attn.in_proj_bias")
             L["o_w"], L["o_b"] = W(p + "self_attn.out_proj.weight"), Bv(p + "self_attn.out_proj.bias")
             ipw, ipb = sd[p + "multihead_attn.in_proj_weight"].detach(), sd[p + "multihead_attn.in_proj_bias"].detach()
-            L["cv_w"], L["cv_b"] = ipw[2 * d:].to(self.dtype).contiguous(), ipb[2 * d:].float().contiguous()
+            L["cv_w"], L["cv_b"] = Wt(ipw[2 * d:]), ipb[2 * d:].float().contiguous()
             L["co_w"], L["co_b"] = W(p + "multihead_attn.out_proj.weight"), Bv(p + "multihead_attn.out_proj.bias")
             L["f1_w"], L["f1_b"] = W(p + "linear1.weight"), Bv(p + "linear1.bias")
             L["f2_w"], L["f2_b"] = W(p + "linear2.weight"), Bv(p + "linear2.bias")
@@ -161,12 +168,13 @@ class DenoiserEngine:
         af = self.buf("prep_af", (BT, d), dt)
         lib.gemm(a, w["ae0_w"], h, bias=w["ae0_b"], act=lib.ACT_MISH)
         lib.gemm(h, w["ae2_w"], af, bias=w["ae2_b"])
+        af_op = lib.split(af) if self.precision == "x3" else af  # (operand of eight GEMMs: split once)
         # audio part of the collapsed cross-attention, per layer
         self.cross = []
         for l in range(P.layers):
             L = w[l]
             c = self.buf(f"cross{l}", (BT, d), dt)
-            lib.gemm(af, L["cv_w"], h, bias=L["cv_b"])
+            lib.gemm(af_op, L["cv_w"], h, bias=L["cv_b"])
             lib.gemm(h, L["co_w"], c, bias=L["co_b"])
             self.cross.append(c)
         # style (+ emotion) per clip and pass, plus positional encoding -> one addend tensor per pass
@@ -252,8 +260,9 @@ class DenoiserEngine:
                      residual=self.addend[0])
             lib.layernorm(x[:BT], x[BT:], r1=self.addend_delta)  # no gamma: a plain row-wise add
         else:
+            x_op = lib.split(x_in) if self.precision == "x3" else x_in
             for s in range(n):
-                lib.gemm(x_in, w["le_w"], x[s * BT:(s + 1) * BT], bias=w["le_b"],
+                lib.gemm(x_op, w["le_w"], x[s * BT:(s + 1) * BT], bias=w["le_b"],
                          act=lib.ACT_MISH if P.latent_mish else lib.ACT_NONE, residual=self.addend[s0 + s])
         scale = 1.0 / math.sqrt(P.dh)
         rows = r1 - r0

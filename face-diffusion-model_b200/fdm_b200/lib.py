@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
                 ("residual", _vp), ("ldr", _i64), ("res_dtype", _i32), ("out_dtype", _i32), ("C", _vp),
                 ("ldc", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("act", _i32), ("taps", _i32),
                 ("tap_k", _i64), ("tap_row_shift", _i64), ("a_ln", _vp), ("w_colsum", _vp), ("res_ln", _vp),
-                ("res_gamma", _vp), ("res_beta", _vp), ("stats_out", _vp)]
+                ("res_gamma", _vp), ("res_beta", _vp), ("stats_out", _vp), ("A_lo", _vp), ("W_lo", _vp)]
 
 
 class NormArgs(C.Structure):
@@ -47,7 +47,7 @@ class DdpmArgs(C.Structure):
     _fields_ = [("x0_cond", _vp), ("x0_uncond", _vp), ("guidance", _f32), ("x_t", _vp), ("noise", _vp),
                 ("out", _vp), ("out_bf16", _vp), ("c1", _vp), ("c2", _vp), ("sigma", _vp), ("t_per_clip", _vp),
                 ("t_dev", _vp), ("B", _i64), ("elems_per_clip", _i64), ("seed", _u64),
-                ("clip_index0", _i64)]
+                ("clip_index0", _i64), ("seed_dev", _vp)]
 
 
 class DdimArgs(C.Structure):
@@ -71,6 +71,7 @@ EXPORTS = {
     "fdm_philox_normal": (C.c_int, [_vp, _i64, _i64, _u64, _i64, _i32, _vp]),
     "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fdm_vq_quantize_ex": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "fdm_split_bf16x2": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "fdm_cast_rows": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "fdm_audio_normalize_pad": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _f32, _vp]),
@@ -149,6 +150,41 @@ def _launched(n: int = 1) -> None:
 
 
 # ------------------------------------------------------------------------------------------------
+class Split:
+    """A tensor as a bf16 pair x = hi + lo (split-bf16 / "bf16x3" operand of the tcgen05 GEMM): fp32-grade products
+    (2^-17 relative) at three tensor-core passes. `hi` and `lo` have identical shapes / strides; indexing slices both."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor):
+        assert hi.dtype == lo.dtype == torch.bfloat16 and hi.shape == lo.shape and hi.stride() == lo.stride()
+        self.hi, self.lo = hi, lo
+
+    def __getitem__(self, idx) -> "Split":
+        return Split(self.hi[idx], self.lo[idx])
+
+    shape = property(lambda self: self.hi.shape)
+    dtype = property(lambda self: "bf16x2")
+
+    def dim(self):
+        return self.hi.dim()
+
+    def stride(self, *a):
+        return self.hi.stride(*a)
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+
+def split(x: torch.Tensor) -> Split:
+    """fp32 tensor (contiguous) -> Split(hi, lo) of the same shape."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+    hi = torch.empty_like(x, dtype=torch.bfloat16)
+    lo = torch.empty_like(x, dtype=torch.bfloat16)
+    _check(require_device().fdm_split_bf16x2(_ptr(x), _ptr(hi), _ptr(lo), x.numel(), _stream()))
+    _launched()
+    return Split(hi, lo)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, *, M: Optional[int] = None,
          lda: Optional[int] = None, a_rows: Optional[int] = None, taps: int = 1, tap_k: int = 0,
@@ -161,6 +197,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     `a` may be any tensor whose storage holds the rows (lda/a_rows/M override the 2-D view for implicit
     convolutions); `out`/`residual` are 2-D with unit inner stride."""
     lib = require_device()
+    a_lo = w_lo = None
+    if isinstance(w, Split):  # split-bf16 operands: A_lo W^T + A W_lo^T + A W^T in one accumulator (fdm_gemm_args.A_lo / W_lo)
+        if not isinstance(a, Split):
+            a = split(a)
+        assert a.hi.data_ptr() % 16 == 0 and a.lo.data_ptr() % 16 == 0
+        a, a_lo, w, w_lo = a.hi, a.lo, w.hi, w.lo
+        assert a_lo.stride() == a.stride() and w_lo.stride() == w.stride()
     assert a.dtype == w.dtype and w.dim() == 2 and w.stride(1) == 1 and out.dim() == 2 and out.stride(1) == 1
     N = w.shape[0]
     Kk = K if K is not None else w.shape[1]
@@ -183,6 +226,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     # LayerNorm folding (bf16 path; see fdm_gemm_args)
     g.a_ln, g.w_colsum, g.res_ln = _ptr(a_ln), _ptr(w_colsum), _ptr(res_ln)
     g.res_gamma, g.res_beta, g.stats_out = _ptr(res_gamma), _ptr(res_beta), _ptr(stats_out)
+    g.A_lo, g.W_lo = _ptr(a_lo), _ptr(w_lo)
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.numel() >= g.M * (N // 64) * 2
     assert out.shape[0] >= g.M and out.shape[1] == N
@@ -264,7 +308,7 @@ def self_attention(q, k, v, out, B: int, T: int, t_stride: int, H: int, dh: int,
 
 def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: float = 0.0, noise=None,
               out_bf16=None, t_per_clip=None, t_dev=None, seed: int = 0,
-              clip_index0: int = 0) -> torch.Tensor:
+              clip_index0: int = 0, seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = require_device()
     a = DdpmArgs()
     B = x_t.shape[0]
@@ -278,6 +322,9 @@ def ddpm_step(x0_cond, x_t, out, c1, c2, sigma, *, x0_uncond=None, guidance: flo
     a.t_per_clip, a.t_dev = _ptr(t_per_clip), _ptr(t_dev)
     a.B, a.elems_per_clip = B, x_t.numel() // B
     a.seed, a.clip_index0 = seed, clip_index0
+    if seed_dev is not None:  # Philox seed read from device memory (int64[1]): replayable graphs, fresh seed per call
+        assert seed_dev.dtype == torch.int64 and seed_dev.numel() == 1
+    a.seed_dev = _ptr(seed_dev)
     _check(lib.fdm_ddpm_step(C.byref(a), _stream()))
     _launched()
     return out

@@ -31,12 +31,15 @@ class SamplerEngine:
     @torch.no_grad()
     def run(self, x_T: torch.Tensor, steps: Sequence[int], noise: NoiseSpec = "philox", seed: int = 0,
             clip_index0: int = 0, graph: bool = True, tap: Optional[Callable[[int, torch.Tensor], None]] = None,
-            time_steps: bool = False, ddim: Optional[dict] = None) -> torch.Tensor:
+            time_steps: bool = False, ddim: Optional[dict] = None, tail=None) -> torch.Tensor:
         """x_T (B, fq*T, zdim) fp32 on device; steps: the t values in execution order (e.g. 999..0).
         noise: "philox" (in-kernel counter-based generator), or a callable t -> tensor (host- or device-side,
         same shape as x_T) that is copied in before every step with t > 0 (parity runs).
         ddim: None for the ancestral (DDPM) update, or per-step device tables {a_recip, a_recipm1, sqrt_an, c} (one
-        entry per element of `steps`) for the deterministic DDIM update (eta = 0, no noise)."""
+        entry per element of `steps`) for the deterministic DDIM update (eta = 0, no noise).
+        tail: None, or (DenoiserEngine prepared for the same clip batch, n): the LAST n steps evaluate the denoiser on that
+        (high-precision, fp32-activation) engine, eagerly, after the graph-replayed bf16 steps - the final latent is the
+        last denoiser output, so its precision is what the quantiser sees (profiles/r02_precision_probe.json)."""
         den = self.den
         B, T, d, S = den.B, den.T, den.P.d, den.passes
         assert x_T.is_cuda and x_T.dtype == torch.float32 and x_T.numel() == B * T * d, "x_T does not match prepare()"
@@ -51,16 +54,22 @@ class SamplerEngine:
         sched.copy_(torch.tensor(steps, dtype=torch.int32), non_blocking=False)
         cursor = den.buf("smp_cursor", (1,), torch.int32, dev)
         t_dev = den.buf("smp_t", (1,), torch.int32, dev)
+        seed_dev = den.buf("smp_seed", (1,), torch.int64, dev)  # Philox seed in device memory: the cached graphs survive a new seed
+        seed_dev.fill_(int(seed))
+        tail_den, n_tail = tail if tail is not None else (None, 0)
+        n_tail = min(n_tail, len(steps))
+        if tail_den is not None:
+            assert (tail_den.B, tail_den.T, tail_den.passes) == (B, T, S) and tail_den.dtype == torch.float32
         host_noise = callable(noise) and ddim is None
         noise_buf = den.buf("smp_noise", tuple(x_T.shape), torch.float32, dev) if host_noise else None
         assert host_noise or ddim is not None or noise in (None, "philox")
 
-        def step_body():
-            x0 = den.denoise(xin, t_dev)
+        def step_body(hi: bool = False):
+            x0 = tail_den.denoise(x.view(B * T, d), t_dev) if hi else den.denoise(xin, t_dev)
             if ddim is None:
                 lib.ddpm_step(x0[0], x, x, self.c1, self.c2, self.sigma, x0_uncond=x0[1] if S == 2 else None,
                               guidance=float(self.level) if S == 2 else 0.0, noise=noise_buf, out_bf16=xin_bf, t_dev=t_dev,
-                              seed=seed, clip_index0=clip_index0)
+                              seed_dev=seed_dev, clip_index0=clip_index0)
             else:
                 lib.ddim_step(x0[0], x, x, ddim["a_recip"], ddim["a_recipm1"], ddim["sqrt_an"], ddim["c"], cursor,
                               x0_uncond=x0[1] if S == 2 else None, guidance=float(self.level) if S == 2 else 0.0,
@@ -79,8 +88,13 @@ class SamplerEngine:
                 n = noise(t)
                 noise_buf.copy_(n.reshape(noise_buf.shape), non_blocking=True)
 
+        main_steps = steps[: len(steps) - n_tail]
+        tail_steps = steps[len(steps) - n_tail:]
+        all_steps, steps = steps, main_steps  # (the device schedule holds every step; the graph loop runs the main ones)
         use_graph = graph and tap is None
-        if use_graph:
+        if use_graph and not steps:
+            reset()
+        elif use_graph:
             # Steps per graph: the step body is the same for every t (t and the schedule cursor live on the device), so
             # when no host data is fed per step several steps are captured back to back in one graph: a slow or busy host
             # then costs one launch per `unroll` steps instead of one per step (measured on a shared box: 880 ms of
@@ -90,7 +104,7 @@ class SamplerEngine:
             # Captured graphs are cached on the denoiser engine, keyed by every address and scalar baked into their nodes
             # (instantiating a 740-node graph costs tens of ms: 18 % of a MEAD job, 3 % of a VOCASET job).
             ddim_key = None if ddim is None else tuple(sorted((k, v.data_ptr()) for k, v in ddim.items()))
-            key = (unroll, S, B, T, seed, clip_index0, self.level, den.pack_serial, den.lanes, host_noise, ddim_key,
+            key = (unroll, S, B, T, seed_dev.data_ptr(), clip_index0, self.level, den.pack_serial, den.lanes, host_noise, ddim_key,
                    x.data_ptr(), xin.data_ptr(), sched.data_ptr(), cursor.data_ptr(), t_dev.data_ptr(),
                    None if noise_buf is None else noise_buf.data_ptr(), self.c1.data_ptr(), self.c2.data_ptr(),
                    self.sigma.data_ptr(), den.x.data_ptr(), den.qkv.data_ptr(), den.att.data_ptr(), den.proj.data_ptr(),
@@ -150,4 +164,9 @@ class SamplerEngine:
                     x0 = den.denoise(xin, t_dev)
                     tap(t, x0.clone())
                 step_body()  # (recomputes the denoiser when tapping: taps are a debugging aid)
+        for t in tail_steps:  # high-precision tail: eager launches on the same loop state, schedule cursor and seed
+            feed_noise(t)
+            if tap is not None:
+                tap(t, tail_den.denoise(x.view(B * T, d), t_dev).clone())
+            step_body(hi=True)
         return x.view(x_T.shape).clone()  # the loop state buffer is reused by the next call

@@ -23,4 +23,4 @@ class FDM(FDMBase):
         self._build(feature_dim, n_head, num_layers, Wav2Vec2Model.from_pretrained(audio_encoder_path))
 
     def forward(self, audio, t, vertice, one_hot):
-        return self._forward(audio, t, vertice, one_hot)[0]
+        return self._forward(audio, t, vertice, one_hot)[0].clone()  # (not a view of the engine's reused output buffer)

@@ -19,7 +19,6 @@ class FDM(FDMBase):
         self._build(feature_dim, n_head, num_layers, HubertModel.from_pretrained(audio_encoder_path))
 
     def forward(self, audio, t, vertice, emotion_one_hot, id_one_hot, mask_cond=False, train=True):
-        guidance = None
-        if mask_cond:  # force_mask semantics of mask_cond (reference :54-62): zero the emotion condition
-            emotion_one_hot = emotion_one_hot * 0
-        return self._forward(audio, t, vertice, id_one_hot, emotion_one_hot, guidance)[0]
+        if mask_cond:  # force_mask semantics of mask_cond (reference :54-62): the null (all-zero) emotion condition
+            emotion_one_hot = self.mask_cond(emotion_one_hot, force_mask=True)
+        return self._forward(audio, t, vertice, id_one_hot, emotion_one_hot, None)[0].clone()  # (not a view of the engine's buffer)

@@ -81,6 +81,13 @@ typedef struct fdm_gemm_args {
   const float* res_beta;   /* [N] */
   float* stats_out;        /* [M][N/64][2]: per 64-column group, sum and sum of squares of the fp32 OUTPUT row values;
                               needs the bf16 residual TMA path and N % 64 == 0, or NULL */
+  /* ---- split-bf16 ("bf16x3") operands (fdm_gemm_bf16 only; both NULL = plain bf16 GEMM) ------------------------------
+   * fp32-grade products on the tensor cores: with x = x_hi + x_lo (fdm_split_bf16x2) the kernel accumulates, in ONE
+   * fp32 TMEM accumulator,  A_lo W^T + A W_lo^T + A W^T  (A / W hold the hi parts; the lo.lo term, 2^-18 relative, is
+   * dropped), i.e. three passes over K inside the same tile. A_lo / W_lo have exactly the layout of A / W (same lda /
+   * a_rows / taps, same ldw). Used by the high-precision steps of the sampler and the once-per-clip audio encoder. */
+  const void* A_lo;
+  const void* W_lo;
 } fdm_gemm_args;
 
 /* TMA-fed tcgen05/TMEM GEMM, bf16 operands, fp32 accumulation. */
@@ -165,6 +172,8 @@ typedef struct fdm_ddpm_args {
   const int64_t* t_per_clip; const int32_t* t_dev;
   int64_t B; int64_t elems_per_clip;
   uint64_t seed; int64_t clip_index0;
+  const uint64_t* seed_dev;  /* optional: the Philox seed is read from device memory instead of `seed`, so a captured
+                                step graph can be replayed with a fresh seed per sampling call */
 } fdm_ddpm_args;
 int fdm_ddpm_step(const fdm_ddpm_args* args, void* stream);
 /* DDIM update (eta = 0), reference diffusion_BIWI_encoder_decoder.py:675-710, fused with the optional CFG combine:
@@ -213,6 +222,8 @@ int fdm_vq_quantize_ex(const float* z, const float* codebook, const int64_t* cod
                        uint64_t* recheck_rows, float* dbg_acc, void* stream);
 
 /* ---- small data-movement kernels ------------------------------------------------------------ */
+/* hi = bf16(x), lo = bf16(x - hi): the operand pair of the split-bf16 GEMM (fdm_gemm_args.A_lo / W_lo). n elements. */
+int fdm_split_bf16x2(const float* src, void* hi, void* lo, int64_t n, void* stream);
 int fdm_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 /* dst[b, l, c] = src[b, c, l] (+ cast); used for VQAutoEncoder.decode's (B,D,L) input. */
 int fdm_transpose_bcl_to_blc(const float* src, void* dst, int32_t dst_dtype,

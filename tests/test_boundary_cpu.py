@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _build_meta(preset):
+    os.environ["FDM_B200_RANDOM_AUDIO_ENCODER"] = "1"  # no checkpoint here: the architecture is what is under test
     with torch.device("meta"):
         if preset == "vocaset":
             from models.fdm_vocaset import FDM
@@ -33,6 +34,22 @@ def _build_meta(preset):
             from video_diffusion_pytorch.diffusion_BIWI_encoder_decoder import GaussianDiffusion
             fdm = FDM(feature_dim=1024, struct="Dec")
         return GaussianDiffusion(fdm, timesteps=1000, loss_type="l2"), VQAutoEncoder(vargs())
+
+
+def test_audio_encoder_random_init_is_opt_in(monkeypatch):
+    """a missing / mistyped checkpoint path must raise like HF's from_pretrained, not silently build a random
+    audio encoder; random initialisation is an explicit request (keyword or FDM_B200_RANDOM_AUDIO_ENCODER=1)."""
+    import warnings
+    from models.hubert import HubertModel
+    monkeypatch.delenv("FDM_B200_RANDOM_AUDIO_ENCODER", raising=False)
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    with pytest.raises(Exception):
+        HubertModel.from_pretrained("/nonexistent/hubert-large-ls960-ft")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.device("meta"):
+            m = HubertModel.from_pretrained("/nonexistent/hubert-large-ls960-ft", random_init=True)
+    assert m.config.hidden_size == 1024 and m.config.num_hidden_layers == 24
 
 
 @pytest.mark.parametrize("preset", ["vocaset", "mead", "biwi"])
@@ -67,7 +84,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/fdm_b200.h but not exported"
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
-    assert handle.fdm_abi_version() == 2
+    assert handle.fdm_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

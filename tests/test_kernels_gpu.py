@@ -378,6 +378,38 @@ def test_vq_tensor_path_bit_exact(cuda_dev, case):
         assert cnt.item() >= 2 * 200   # the rows sitting on duplicated codes must have gone through it
 
 
+@pytest.mark.parametrize("D", [64, 128])
+def test_vq_nan_inf_rows_are_defined(cuda_dev, D):
+    """A diverged sample (NaN / +-Inf latent rows) must not fault: no distance compares below +inf, so such a row takes
+    code 0 on BOTH kernels (torch.argmin never crashes either; oracle/vq_ref.c starts from index 0), and every other
+    row keeps the oracle's index (the FFMA kernel indexed shared memory with 0x7fffffff)."""
+    from fdm_b200 import lib
+    from oracle import reference_ops as R  # checker
+    gen = torch.Generator(device="cpu").manual_seed(11 + D)
+    B, L, n = 2, 300, 256
+    z = torch.randn(B, L, D, generator=gen)
+    cb = torch.randn(n, D, generator=gen)
+    bad = [3, 64, 65, 127, 128, 299]
+    z[0, bad[0]] = float("nan")
+    z[0, bad[1], 5] = float("inf")
+    z[0, bad[2], 0] = float("-inf")
+    z[1, bad[3]] = float("inf")
+    z[1, bad[4], D - 1] = float("nan")
+    z[1, bad[5]] = float("nan")
+    algos = [lib.VQ_FFMA] + ([lib.VQ_TENSOR] if D == 64 else [])
+    for algo in algos:
+        idx, zq, zr = lib.vq_quantize(z.to(cuda_dev), cb.to(cuda_dev), n, want_rows=True, algo=algo)
+        torch.cuda.synchronize()  # an out-of-bounds shared-memory read would surface here as a sticky fault
+        idx = idx.view(B, L).cpu()
+        assert int(idx.min()) >= 0 and int(idx.max()) < n
+        for b in range(B):
+            ref, _, _ = R.vq_quantize(z[b], cb)
+            assert torch.equal(idx[b], ref), (algo, b, (idx[b] != ref).nonzero()[:5].tolist())
+        for b, r in ((0, bad[0]), (0, bad[1]), (0, bad[2]), (1, bad[3]), (1, bad[4]), (1, bad[5])):
+            assert idx[b, r] == 0
+            assert torch.equal(zr[b, r].cpu(), cb[0])
+
+
 def test_vq_tensor_dot_error_bound(cuda_dev):
     """Measures the error of the tensor-core scores a_j = z.e_j - ee_j/2 (bf16x3 products + a bf16x3 image of -ee_j/2,
     fp32 accumulation in TMEM) against fp64 and checks it sits well inside the budget the kernel's candidate window

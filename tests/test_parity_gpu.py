@@ -192,6 +192,59 @@ def test_classifier_free_guidance(cuda_dev, preset):
     assert (out[0].cpu() - ref).abs().max().item() < 2e-4
 
 
+def test_mead_forward_mask_cond_kwarg(cuda_dev):
+    """forward(..., mask_cond=True) of the MEAD FDM (reference signature models/fdm_vqvae_mead.py:65): the emotion
+    condition is replaced by mask_cond(force_mask=True) = zeros, i.e. the unconditional pass of the guidance."""
+    from oracle import reference_ops as R
+    fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup("mead", cuda_dev, "fp32")
+    g = golden("mead")
+    x = torch.from_numpy(g["x_T"])[None].to(cuda_dev)
+    tt = torch.full((1,), 321, dtype=torch.long, device=cuda_dev)
+    y_u = fdm(audio, tt, x, emo, idh, mask_cond=True)
+    y_c = fdm(audio, tt, x, emo, idh, mask_cond=False, train=False)
+    ref_u = R.fdm_forward(sd, "mead", hiddens[0], 321, x[0].cpu(), idh.cpu(), torch.zeros_like(emo).cpu())
+    ref_c = R.fdm_forward(sd, "mead", hiddens[0], 321, x[0].cpu(), idh.cpu(), emo.cpu())
+    assert (y_u[0].cpu() - ref_u).abs().max().item() < 1e-4
+    assert (y_c[0].cpu() - ref_c).abs().max().item() < 1e-4
+    assert (ref_u - ref_c).abs().max().item() > 1e-3  # the condition matters, so the two checks are distinct
+    assert y_u.data_ptr() != y_c.data_ptr()  # forward() returns its own tensor, not a view of the engine's reused buffer
+    both = fdm._forward(audio, tt, x, idh, emo, guidance="emotion")  # the batched guidance passes
+    assert torch.equal(both[1], y_u) and torch.equal(both[0], y_c)
+    z = torch.ones(2, 7, device=cuda_dev)
+    assert torch.equal(fdm.mask_cond(z, force_mask=True), torch.zeros_like(z)) and torch.equal(fdm.mask_cond(z), z)
+
+
+def test_decode_shortcut_follows_the_tensor_not_its_address(cuda_dev):
+    """decode() reused the row buffer of an earlier quant() for ANY tensor at the same address. The rows now
+    travel with the tensor object quant() returned; a different tensor at a recycled address must be decoded itself."""
+    from helpers import build_vqvae
+    ae = build_vqvae("vocaset", device=cuda_dev)
+    ae.set_precision("fp32")
+    g = torch.Generator(device="cpu").manual_seed(8)
+    z1 = torch.randn(1, 16 * 6, 64, generator=g).to(cuda_dev)
+    z2 = torch.randn(1, 16 * 6, 64, generator=g).to(cuda_dev)
+    zq1, _, _ = ae.quant(z1)
+    v1 = ae.decode(zq1)                      # shortcut path
+    v1b = ae.decode(zq1.clone())             # same values, no attached rows: transpose path
+    assert torch.equal(v1, v1b)
+    zq2_ref, _, _ = ae.quant(z2)
+    v2_ref = ae.decode(zq2_ref)
+    shape, ptr = zq1.shape, zq1.data_ptr()
+    del zq1
+    other = None
+    for _ in range(8):  # the caching allocator hands the freed block to the next tensor of that size
+        other = torch.empty(shape, device=cuda_dev)
+        if other.data_ptr() == ptr:
+            break
+    other.copy_(zq2_ref)
+    v2 = ae.decode(other)
+    assert torch.equal(v2, v2_ref) and not torch.equal(v2, v1)
+    zq3, _, _ = ae.quant(z1)
+    zq3.mul_(1.0)                            # in-place update bumps the version: the attached rows are stale
+    assert getattr(zq3, "_fdm_rows")[1] != zq3._version
+    assert torch.equal(ae.decode(zq3), v1)
+
+
 def test_philox_device_matches_host_reference(cuda_dev):
     from fdm_b200 import lib
     from oracle.philox_ref import philox_normal
@@ -272,8 +325,8 @@ def test_audio_frontend_and_vertex_metrics(cuda_dev):
 
 def test_cached_step_graphs_are_reused_and_keyed(cuda_dev):
     """Step graphs are cached per batch shape on the denoiser engine (persistent buffers, stable addresses): a second job
-    of the same shape must replay the cached graph and reproduce a freshly captured run bit for bit, new audio must give
-    new results through the same graph, and anything baked into the graph nodes (the Philox seed) must miss the cache."""
+    of the same shape must replay the cached graph and reproduce a freshly captured run bit for bit, new audio and a new
+    Philox seed (device-resident) must give new results through the same graph (sampling noise was frozen)."""
     from oracle.weights import host_noise
     clips = (0, 1)
     fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup("vocaset", cuda_dev, "bf16", clips=clips)
@@ -290,9 +343,16 @@ def test_cached_step_graphs_are_reused_and_keyed(cuda_dev):
     assert len(eng.graph_cache) == 1 and torch.equal(a, b)
     c = diff.p_sample_loop(shape, (audio * 0.5).contiguous(), idh, x_T=xT, steps=steps)
     assert len(eng.graph_cache) == 1 and not torch.equal(a, c)
-    diff.seed = 6
+    diff.seed = 6  # the Philox seed lives in device memory: a new seed replays the SAME graph with new noise
     d = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)
-    assert len(eng.graph_cache) == 2 and not torch.equal(a, d)
+    assert len(eng.graph_cache) == 1 and not torch.equal(a, d)
+    diff.seed = None  # default: a fresh seed per call from torch's generator - independent draws, reproducible by manual_seed
+    torch.manual_seed(123)
+    r1 = diff.p_sample_loop(shape, audio.clone(), idh, steps=steps)
+    r2 = diff.p_sample_loop(shape, audio.clone(), idh, steps=steps)
+    torch.manual_seed(123)
+    r3 = diff.p_sample_loop(shape, audio.clone(), idh, steps=steps)
+    assert not torch.equal(r1, r2) and torch.equal(r1, r3) and len(eng.graph_cache) == 1
     diff.seed = 5
     eng.graph_cache.clear()
     e = diff.p_sample_loop(shape, audio.clone(), idh, x_T=xT, steps=steps)  # fresh capture
