@@ -347,8 +347,14 @@ class GaussianDiffusionBase(nn.Module):
         self.seed = None
         self.clip_index0 = 0
         self.use_cuda_graph = True
-        self.last_step_ms = None
+        self.__dict__["_last_sampler"] = None
         self.__dict__["_sigma"] = None
+
+    @property
+    def last_step_ms(self):
+        """Median device ms per denoising step of the last sampling call (needs `self.time_steps = True`)."""
+        smp = self.__dict__.get("_last_sampler")
+        return None if smp is None else smp.step_ms()
 
     # -- helpers ---------------------------------------------------------------------------------------
     def _sigma_table(self) -> torch.Tensor:
@@ -426,7 +432,7 @@ class GaussianDiffusionBase(nn.Module):
         out = sampler.run(x_T, steps, noise=self.noise_source, seed=seed, clip_index0=self.clip_index0,
                           graph=self.use_cuda_graph, tap=tap, time_steps=getattr(self, "time_steps", False),
                           tail=self._tail(fdm, audio, shape[1] // P.fq, idh, emo, gcond, len(steps)))
-        self.last_step_ms = sampler.last_step_ms
+        self.__dict__["_last_sampler"] = sampler
         return out
 
     @torch.inference_mode()
@@ -461,7 +467,7 @@ class GaussianDiffusionBase(nn.Module):
         out = sampler.run(x_T, [p[0] for p in pairs], graph=self.use_cuda_graph, tap=tap, ddim=tables,
                           time_steps=getattr(self, "time_steps", False),
                           tail=self._tail(fdm, audio, shape[1] // P.fq, idh, emo, gcond, len(pairs)))
-        self.last_step_ms = sampler.last_step_ms
+        self.__dict__["_last_sampler"] = sampler
         return out
 
     @torch.inference_mode()

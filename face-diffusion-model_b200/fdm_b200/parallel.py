@@ -61,7 +61,7 @@ class OverlappedDecodeGather:
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         assert out.dim() == 4 and out.shape[0] == world and out.is_contiguous()
         B_local = out.shape[1]
-        n = min(self.chunks, B_local)
+        n = min(self.chunks, B_local) if world > 1 else 1  # a single rank decodes in one pass: nothing to overlap
         bounds = [B_local * i // n for i in range(n + 1)]
         cur = torch.cuda.current_stream()
         if world > 1 and (self._stream is None or self._stream.device != out.device):

@@ -26,7 +26,19 @@ class SamplerEngine:
         self.c1, self.c2, self.sigma = c1, c2, sigma
         self.level = guidance_level
         self.last_step_ms = None
+        self._step_events = None
         self.steps_per_graph = int(os.environ.get("FDM_B200_STEPS_PER_GRAPH", "10"))
+
+    def step_ms(self):
+        """Median device time of one denoising step of the last run(time_steps=True), from the CUDA events recorded around
+        every graph replay (waits for the last of them)."""
+        if self._step_events is not None:
+            evs, unroll = self._step_events
+            evs[-1].synchronize()
+            ms = sorted(evs[i].elapsed_time(evs[i + 1]) / unroll for i in range(len(evs) - 1))
+            self.last_step_ms = ms[len(ms) // 2]
+            self._step_events = None
+        return self.last_step_ms
 
     @torch.no_grad()
     def run(self, x_T: torch.Tensor, steps: Sequence[int], noise: NoiseSpec = "philox", seed: int = 0,
@@ -153,9 +165,7 @@ class SamplerEngine:
                 g1.replay()
                 lib._launched(per_step)
             if evs is not None and n_rep > 0:
-                torch.cuda.synchronize()
-                ms = sorted(evs[i].elapsed_time(evs[i + 1]) / unroll for i in range(n_rep))
-                self.last_step_ms = ms[len(ms) // 2]
+                self._step_events = (evs, unroll)  # read lazily (step_ms): no synchronisation inside the sampling job
         else:
             reset()
             for t in steps:

@@ -126,9 +126,11 @@ def _denoiser(fdm, preset: str, T: int, fq: int, zdim: int, guidance: bool, leve
     return Wrapped().eval()
 
 
-def time_sampling(preset: str, seconds: float, n_steps: int, total_steps: int, guidance: bool, threads: int):
-    """One clip through the reference as its sample scripts run it, `n_steps` DDPM steps (t = 999 ...), plus quantise +
-    decode; extrapolated to `total_steps`. Returns dict(fps, frames, s_per_step, quant_decode_s, cores)."""
+def time_sampling(preset: str, seconds: float, n_steps: int, total_steps: int, guidance: bool, threads: int,
+                  samples: int = 1, warmup_samples: int = 0, warmup_steps: int = 2):
+    """One clip through the reference as its sample scripts run it. A SAMPLE = `n_steps` DDPM steps (t = 998 ...) through
+    `diffusion.p_sample` plus quantise + decode, extrapolated to `total_steps`; `warmup_samples` shorter untimed samples
+    first. Returns a list of dicts (one per timed sample): fps, frames, s_per_step, quant_decode_s, sample_s, cores."""
     import torch
     torch.set_num_threads(threads)
     fdm, ae, diff = build(preset)
@@ -148,26 +150,31 @@ def time_sampling(preset: str, seconds: float, n_steps: int, total_steps: int, g
     T = N // 2 if pair else N
     shape = (1, T * fq, zdim)
     diff.denoise_fn = _denoiser(fdm, preset, T, fq, zdim, guidance)
-    x = torch.randn(shape)
-    t0 = time.perf_counter()
-    x = diff.p_sample(x, torch.full((1,), 999, dtype=torch.long), audio, *conds)  # warm-up step
-    warm = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    for i in range(n_steps):
-        x = diff.p_sample(x, torch.full((1,), 998 - i, dtype=torch.long), audio, *conds)
-    per_step = (time.perf_counter() - t0) / n_steps
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        q = ae.quant(x, conds[0]) if preset == "mead" else ae.quant(x)
-        v = ae.decode(q[0])
-    tail = time.perf_counter() - t0
-    assert v.shape[1] == T
-    total = per_step * total_steps + tail
-    return dict(fps=T / total, frames=T, s_per_step=per_step, quant_decode_s=tail, cores=threads, warmup_step_s=warm,
-                sampled_steps=n_steps)
+
+    def one(steps):
+        x = torch.randn(shape)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            x = diff.p_sample(x, torch.full((1,), 998 - i, dtype=torch.long), audio, *conds)
+        loop = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            q = ae.quant(x, conds[0]) if preset == "mead" else ae.quant(x)
+            v = ae.decode(q[0])
+        tail = time.perf_counter() - t1
+        assert v.shape[1] == T
+        per_step = loop / steps
+        return dict(fps=T / (per_step * total_steps + tail), frames=T, s_per_step=per_step, quant_decode_s=tail,
+                    sample_s=loop + tail, cores=threads, sampled_steps=steps)
+
+    for _ in range(warmup_samples):
+        one(warmup_steps)
+    return [one(n_steps) for _ in range(samples)]
 
 
-if __name__ == "__main__":  # python oracle/ref_runner.py preset seconds n_steps total_steps guidance threads -> one JSON line
+if __name__ == "__main__":
+    # python oracle/ref_runner.py preset seconds n_steps total_steps guidance threads [samples warmup_samples] -> JSON list
     import json
     a = sys.argv[1:]
-    print(json.dumps(time_sampling(a[0], float(a[1]), int(a[2]), int(a[3]), a[4] == "1", int(a[5]))))
+    print(json.dumps(time_sampling(a[0], float(a[1]), int(a[2]), int(a[3]), a[4] == "1", int(a[5]),
+                                   int(a[6]) if len(a) > 6 else 1, int(a[7]) if len(a) > 7 else 0)))
