@@ -6,6 +6,7 @@
 
 int fdm_attention_mma_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);  // attention_mma.cu
 int fdm_attention_tc_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);   // attention_tc.cu
+int fdm_attention_tc2_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);  // attention_tc2.cu
 
 namespace {
 
@@ -157,7 +158,9 @@ extern "C" int fdm_self_attention(const fdm_attn_args* args, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a.dtype == FDM_BF16) {
     bool handled = false;
-    int rc = fdm_attention_tc_try(a, s, &handled);   // tcgen05/TMEM kernel: causal, head dim 128, T <= 208
+    int rc = fdm_attention_tc2_try(a, s, &handled);  // tcgen05/TMEM kernel, 16 softmax warps: head dim 128, T <= 208, causal or unmasked
+    if (rc != 0 || handled) return rc;
+    rc = fdm_attention_tc_try(a, s, &handled);       // first-generation tcgen05 kernel (FDM_B200_ATTN_TC=1)
     if (rc != 0 || handled) return rc;
     rc = fdm_attention_mma_try(a, s, &handled);      // mma.sync kernel: head dim 64 / 128, any bias mode
     if (rc != 0 || handled) return rc;

@@ -438,7 +438,7 @@ bool make_map3(CUtensorMap* out, const void* ptr, int64_t cols, int64_t T, int64
 
 int fdm_attention_tc_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled) {
   *handled = false;
-  static const bool enabled = [] { const char* e = getenv("FDM_B200_ATTN_TC"); return !(e && e[0] == '0'); }();
+  static const bool enabled = [] { const char* e = getenv("FDM_B200_ATTN_TC"); return !(e && e[0] == '0'); }();  // (default path: attention_tc2.cu; this kernel runs when that one declines or FDM_B200_ATTN_TC=1)
   if (!enabled || a.dtype != FDM_BF16 || a.dh != DH || a.bias_mode != 1 || a.T > TK_MAX || a.T < 16 || a.H > H_MAX) return 0;
   // Q, K, V must be the three column groups of ONE packed [rows, 3d] buffer (what the denoiser's in_proj GEMM writes)
   const int64_t d = a.H * a.dh;

@@ -225,7 +225,12 @@ def _alibi_mask(H, T, period):
 
 
 @pytest.mark.parametrize("H,dh,T,causal", [(8, 128, 198, True), (4, 128, 99, True), (4, 256, 149, True),
-                                            (8, 128, 70, False), (16, 64, 198, False)])
+                                            (8, 128, 70, False), (16, 64, 198, False),
+                                            # tcgen05 kernel edge shapes: one / two query tiles, ragged and full last key chunk,
+                                            # the unmasked EVQ-VAE decoder attention at 4 s / 8 s (T = 198 / 199)
+                                            (8, 128, 128, True), (8, 128, 129, True), (8, 128, 208, True), (4, 128, 16, True),
+                                            (4, 128, 161, True), (8, 128, 198, False), (8, 128, 199, False), (8, 128, 208, False),
+                                            (8, 128, 128, False), (8, 128, 144, False)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_attention(cuda_dev, H, dh, T, causal, dtype):
     from fdm_b200 import lib
