@@ -50,5 +50,5 @@ extern "C" int fdm_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc
   if (cc_major) *cc_major = major;
   if (cc_minor) *cc_minor = minor;
   FDM_CHECK_ARG(major == 10, "libfdm_b200 is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
-  return 0;
+  return fdm_gemm_init_device();  // per-device constants (allocated here, never inside a stream capture)
 }

@@ -30,6 +30,8 @@ void fdm_set_error(const char* fmt, ...);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+const void* fdm_gemm_identity();  // 64 x 64 bf16 identity of the current device (gemm_tc.cu), or nullptr before fdm_gemm_init_device()
+int fdm_gemm_init_device();
 int fdm_sm_count();  // cached multiprocessor count of the current device
 bool fdm_pdl_enabled();  // programmatic dependent launch for the hot-loop kernels (on by default; env FDM_B200_PDL=0 turns it off)
 

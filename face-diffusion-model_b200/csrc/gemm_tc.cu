@@ -25,6 +25,8 @@ constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int EPI_WARPS = 8;
 constexpr int ACC_STAGES = 2;
 constexpr int NB_STAGE = 2;  // epilogue staging tiles per warp
+constexpr int IDENT_COPIES = 256;  // copies of the 64 x 64 identity in global memory (RESMMA): every CTA reads its own copy, so
+                                   // the loads spread over the L2 slices instead of hammering the 64 lines of a single one
 
 // CG = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
 // CG = 2: a CTA pair (cluster of 2 SMs) per 256 x BLOCK_N tile (cta_group::2): each CTA stages its own 128 rows of A and
@@ -351,15 +353,31 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BLOCK_N, int CG, bool FOLD>
+// Tensor maps of the low halves of split-bf16 operands. The plain kernels carry an empty struct: a producer that picks its
+// tensor map through a run-time pointer select (even one that always resolves to the same map) issues TMA loads measurably
+// slower - the QKV GEMM of the VOCASET step went from 111.6 to 124.2 us (A/B on one box, profiles/r02_b_gemm_ab.md) - so
+// SPLIT is a template parameter and the plain instantiation is instruction-for-instruction the single-map kernel.
+template <bool SPLIT> struct LoMaps {};
+template <> struct LoMaps<true> { CUtensorMap a, b; };
+// RESMMA: the bf16 residual is added BY THE TENSOR CORE. After the K loop of a tile the producer streams the residual
+// tile through the operand ring as BLOCK_N / 64 extra k-blocks (A slot: residual[128 rows, 64 columns], B slot: a 64 x 64
+// identity from a tiny L2-resident matrix) and the issuer accumulates each into its 64-column slice of the TMEM
+// accumulator with N = 64 MMAs: D[:, 64 j + n] += sum_k R[:, 64 j + k] I[n, k]. bf16 x 1.0 is exact in the fp32
+// accumulator, so the result equals the epilogue add up to fp32 summation order, the tile costs one k-block equivalent
+// more of MMA time (+6 % at K = 1024), and the epilogue is the plain one: the TMA-residual epilogue took 11-16k cycles
+// per 256 x 256 tile against 8k cycles of MMA (profiles/r01_j_gemm_tc_full.md: tensor pipe 60 % on the out-projection).
+template <bool RESMMA> struct ResMaps {};
+template <> struct ResMaps<true> { CUtensorMap res, ident; };
+
+template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-               const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_b_lo, const Epilogue ep,
+               const __grid_constant__ LoMaps<SPLIT> lo, const __grid_constant__ ResMaps<RESMMA> rm, const Epilogue ep,
                const int M, const int N, const int num_k_blocks, const int kb_per_tap, const int tap_row_shift, const int m_tiles,
                const int n_tiles, const int kb_per_seg) {
-  // num_k_blocks = segments x kb_per_seg. One segment: the plain bf16 GEMM. Three segments (split-bf16 operands): the same
-  // K range three times into the same accumulator - A_lo W_hi, A_hi W_lo, A_hi W_hi (small terms first) - only the
+  // num_k_blocks = segments x kb_per_seg. One segment: the plain bf16 GEMM. Three segments (SPLIT, split-bf16 operands): the
+  // same K range three times into the same accumulator - A_lo W_hi, A_hi W_lo, A_hi W_hi (small terms first) - only the
   // producer's choice of tensor map differs, the MMA issuer and the epilogue see one long K loop.
   using C = Cfg<BLOCK_N, CG>;
   extern __shared__ uint8_t smem_raw[];
@@ -387,7 +405,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b);
     if (ep.tma_c) tma_prefetch_desc(&tmap_c);
     if (ep.tma_r) tma_prefetch_desc(&tmap_r);
-    if (kb_per_seg != num_k_blocks) { tma_prefetch_desc(&tmap_a_lo); tma_prefetch_desc(&tmap_b_lo); }
+    if constexpr (SPLIT) { tma_prefetch_desc(&lo.a); tma_prefetch_desc(&lo.b); }
+    if constexpr (RESMMA) { tma_prefetch_desc(&rm.res); tma_prefetch_desc(&rm.ident); }
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), CG);  // CG = 2: leader's expect_tx arrival + the peer's remote arrival
@@ -423,12 +442,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const int seg = kb / kb_per_seg;       // 0 for a plain GEMM
-          const int ks = kb - seg * kb_per_seg;  // k-block inside the segment
+          const CUtensorMap* ma = &tmap_a;
+          const CUtensorMap* mb = &tmap_b;
+          int ks = kb;  // k-block inside the segment
+          if constexpr (SPLIT) {
+            const int seg = kb / kb_per_seg;
+            ks = kb - seg * kb_per_seg;
+            if (seg == 0) ma = &lo.a;
+            if (seg == 1) mb = &lo.b;
+          }
           const int tap = ks / kb_per_tap;
           const int kc = ks - tap * kb_per_tap;
-          const CUtensorMap* ma = (kb_per_seg != num_k_blocks && seg == 0) ? &tmap_a_lo : &tmap_a;
-          const CUtensorMap* mb = seg == 1 ? &tmap_b_lo : &tmap_b;
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           if (CG == 1) {
             mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -442,6 +466,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (cta_rank != 0) mbar_arrive_remote(full_bar(stage), 0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if constexpr (RESMMA) {  // residual tile as BLOCK_N / 64 identity k-blocks
+          constexpr uint32_t RES_TX = C::A_BYTES + (64 / CG) * 128;
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
+            const int col = n_blk * BLOCK_N + 64 * j;
+            if (col >= N) break;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + stage * C::STAGE_BYTES;
+            if (CG == 1) {
+              mbar_expect_tx(full_bar(stage), RES_TX);
+              tma_load_2d(sa, &rm.res, full_bar(stage), col, a_row);
+              tma_load_2d(sa + C::A_BYTES, &rm.ident, full_bar(stage), 0, static_cast<int>(blockIdx.x % IDENT_COPIES) * 64);
+            } else {
+              if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * RES_TX);
+              tma_load_2d_2sm(sa, &rm.res, full_bar(stage), col, a_row);
+              tma_load_2d_2sm(sa + C::A_BYTES, &rm.ident, full_bar(stage), 0,
+                              static_cast<int>(blockIdx.x % IDENT_COPIES) * 64 + static_cast<int>(cta_rank) * 32);
+              if (cta_rank != 0) mbar_arrive_remote(full_bar(stage), 0);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -471,6 +516,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (CG == 2) umma_commit_2sm(empty_bar(stage));
           else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if constexpr (RESMMA) {
+          constexpr uint32_t idesc64 = make_idesc_bf16_f32(BLOCK_M * CG, 64);
+          const int n_blk = tile % n_tiles;
+          for (int j = 0; j < BLOCK_N / 64; ++j) {
+            if (n_blk * BLOCK_N + 64 * j >= N) break;
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sa = base + stage * C::STAGE_BYTES;
+            const uint64_t adesc = make_kmajor_sw128_desc(sa);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if (CG == 2) umma_bf16_2sm(tmem_d + 64u * j, adesc + 2u * k, bdesc + 2u * k, idesc64, 1u);
+              else umma_bf16(tmem_d + 64u * j, adesc + 2u * k, bdesc + 2u * k, idesc64, 1u);
+            }
+            if (CG == 2) umma_commit_2sm(empty_bar(stage));
+            else umma_commit(empty_bar(stage));
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
         // accumulator complete -> epilogue (of both CTAs when CG = 2)
         if (CG == 2) umma_commit_2sm(tfull_bar(acc));
@@ -748,13 +813,29 @@ int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int BLOCK_N, int CG, bool FOLD>
-int launch_impl(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
+// IDENT_COPIES x (64 x 64 bf16 identity) (the B operand of the residual k-blocks), per device, created by fdm_device_info()
+void* g_identity[64] = {nullptr};
+
+template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA>
+int launch_impl(const fdm_gemm_args& a, const Epilogue& ep_in, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
+  }
+  Epilogue ep = ep_in;
+  ResMaps<RESMMA> rm;
+  if constexpr (RESMMA) {  // the residual goes through the tensor core: the epilogue sees a GEMM without one
+    if (!fdm_gemm_identity()) {  // a device fdm_device_info() was never called on (allocates: not during stream capture)
+      if (int rc = fdm_gemm_init_device()) return rc;
+    }
+    const void* ident = fdm_gemm_identity();
+    if (int rc = make_tmap(&rm.res, a.residual, a.N, a.M, a.ldr, BLOCK_M)) return rc;
+    if (int rc = make_tmap(&rm.ident, ident, 64, 64 * IDENT_COPIES, 64, 64 / CG)) return rc;
+    ep.residual = nullptr;
+    ep.tma_r = 0;
+    ep.vec_r = 0;
   }
   const int taps = a.taps > 1 ? a.taps : 1;
   const int64_t a_cols = taps > 1 ? a.tap_k : a.K;
@@ -771,34 +852,63 @@ int launch_impl(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream)
   if (ep.tma_r) {
     if (int rc = make_tmap(&tm_r, a.residual, a.N, a.M, a.ldr, 32, 64, false)) return rc;
   }
-  const bool split = a.A_lo != nullptr;
-  CUtensorMap tm_a_lo = tm_a, tm_b_lo = tm_b;
-  if (split) {
-    if (int rc = make_tmap(&tm_a_lo, a.A_lo, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
-    if (int rc = make_tmap(&tm_b_lo, a.W_lo, a.K, a.N, a.ldw, BLOCK_N / CG)) return rc;
+  LoMaps<SPLIT> lo;
+  if constexpr (SPLIT) {
+    if (int rc = make_tmap(&lo.a, a.A_lo, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
+    if (int rc = make_tmap(&lo.b, a.W_lo, a.K, a.N, a.ldw, BLOCK_N / CG)) return rc;
   }
   const int m_tiles = static_cast<int>(ceil_div64(a.M, BLOCK_M * CG));
   const int n_tiles = static_cast<int>(ceil_div64(a.N, BLOCK_N));
   const int kb_per_seg = static_cast<int>(ceil_div64(a.K, BLOCK_K));
-  const int num_k_blocks = kb_per_seg * (split ? 3 : 1);
+  const int num_k_blocks = kb_per_seg * (SPLIT ? 3 : 1);
   const int kb_per_tap = taps > 1 ? static_cast<int>(a.tap_k / BLOCK_K) : kb_per_seg;
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
   static const int sm_limit = [] { const char* e = getenv("FDM_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();  // experiments only
   const int64_t slots = (sm_limit > 0 ? sm_limit : fdm_sm_count()) / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
   const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
-  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
-                                tm_c, tm_r, tm_a_lo, tm_b_lo, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks,
+  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
+                                tm_c, tm_r, lo, rm, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks,
                                 kb_per_tap, taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles, kb_per_seg));
   return 0;
 }
 
 template <int BLOCK_N, int CG = 1>
 int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
-  if (ep.a_ln || ep.res_ln || ep.stats_out) return launch_impl<BLOCK_N, CG, true>(a, ep, stream);
-  return launch_impl<BLOCK_N, CG, false>(a, ep, stream);
+  if (a.A_lo) {  // split-bf16 operands (never combined with LayerNorm folding)
+    FDM_CHECK_ARG(!(ep.a_ln || ep.res_ln || ep.stats_out), "fdm_gemm_bf16: split-bf16 operands cannot be combined with LayerNorm folding");
+    return launch_impl<BLOCK_N, CG, false, true, false>(a, ep, stream);
+  }
+  if (ep.a_ln || ep.res_ln || ep.stats_out) return launch_impl<BLOCK_N, CG, true, false, false>(a, ep, stream);
+  // bf16 residual without an activation: optionally added by the tensor core (FDM_B200_GEMM_RESMMA=1; default: the
+  // TMA-residual epilogue)
+  static const bool resmma = [] { const char* e = getenv("FDM_B200_GEMM_RESMMA"); return e && e[0] == '1'; }();
+  if (resmma && a.residual && a.res_dtype == FDM_BF16 && a.act == FDM_ACT_NONE && aligned16(a.residual) && (a.ldr * 2) % 16 == 0)
+    return launch_impl<BLOCK_N, CG, false, false, true>(a, ep, stream);
+  return launch_impl<BLOCK_N, CG, false, false, false>(a, ep, stream);
 }
 
 }  // namespace
+
+const void* fdm_gemm_identity() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_identity[dev];
+}
+int fdm_gemm_init_device() {  // not during stream capture: allocates
+  int dev = 0;
+  FDM_CHECK_CUDA(cudaGetDevice(&dev));
+  FDM_CHECK_ARG(dev >= 0 && dev < 64, "fdm_gemm_init_device: device index %d out of range", dev);
+  if (g_identity[dev]) return 0;
+  static uint16_t host[64 * 64];
+  for (int i = 0; i < 64; ++i)
+    for (int j = 0; j < 64; ++j) host[i * 64 + j] = i == j ? 0x3F80 : 0;  // bf16(1.0)
+  void* p = nullptr;
+  FDM_CHECK_CUDA(cudaMalloc(&p, sizeof(host) * IDENT_COPIES));
+  for (int c = 0; c < IDENT_COPIES; ++c)
+    FDM_CHECK_CUDA(cudaMemcpy(static_cast<uint8_t*>(p) + sizeof(host) * c, host, sizeof(host), cudaMemcpyHostToDevice));
+  g_identity[dev] = p;
+  return 0;
+}
 
 extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   FDM_CHECK_ARG(args != nullptr, "fdm_gemm_bf16: null args");

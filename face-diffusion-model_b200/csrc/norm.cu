@@ -1,6 +1,7 @@
 // Row LayerNorm with fused residual adds (one warp per row, values kept in registers, two-pass
 // mean/variance in fp32) and LeakyReLU + InstanceNorm over time for the VQ-decoder expander.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -280,6 +281,243 @@ bool try_fast_ln(const fdm_norm_args& a, cudaStream_t s) {
   return false;
 }
 
+// ---- hot-loop LayerNorm kernels of the denoiser step (bf16, d in {512, 1024}) ------------------------------------------
+// The warp-per-two-rows kernel above ran at 2.9-4.0 TB/s: 125 registers (16 warps per SM), ~720 warp instructions per row of
+// the fused pair (gamma / beta re-read from L1 for every row pair, the cross-attention rows fetched only after the first
+// LayerNorm), long-scoreboard bound (profiles/r01_i_layernorm_full.md). Two kernels replace it:
+//   * plain LayerNorm (norm3): column-owner layout. A thread owns 8 consecutive columns (one 16-byte chunk) of R rows, d / 8
+//     threads cover a row; gamma / beta of those columns live in registers, every load of the CTA is in flight before the
+//     first use, row statistics are a reduce-scatter over the R rows a lane holds plus one shared-memory exchange between the
+//     d / 256 warps of a row.
+//   * fused pair (norm1 -> + cross-attention cache + time row -> norm2): one warp per row, x and the cache row loaded up
+//     front, gamma / beta / (beta1 + time row) staged once per CTA in shared memory, ~75 registers (24+ warps per SM), no
+//     block-wide synchronisation in the row loop.
+// Row statistics are (mean, M2) pairs merged with Chan's equal-count formula: two-pass accuracy in one reduction.
+__device__ __forceinline__ void chan_merge(float& m, float& q, float rm, float rq, float n_half) {
+  const float dl = rm - m;
+  m = fmaf(0.5f, dl, m);
+  q = fmaf(dl * dl, n_half, q + rq);
+}
+template <int R>
+__device__ __forceinline__ void stat_reduce_scatter(float (&m)[R], float (&q)[R], int lane) {
+  // in: per-lane (mean, M2) of 8 elements of each of R rows. out: m[0], q[0] = the statistics of 256 elements of row
+  // `stat_row<R>(lane)`, identical in the 32 / R lanes that share that row.
+  float n_half = 4.f;  // half the element count of each side of a merge
+  int half = R / 2;
+#pragma unroll
+  for (int mask = 16; mask >= 1; mask >>= 1) {
+    if (half >= 1) {
+      const bool up = (lane & mask) != 0;
+#pragma unroll
+      for (int i = 0; i < R / 2; ++i) {
+        if (i < half) {
+          const float sm = up ? m[i] : m[i + half], sq = up ? q[i] : q[i + half];
+          float km = up ? m[i + half] : m[i], kq = up ? q[i + half] : q[i];
+          chan_merge(km, kq, __shfl_xor_sync(0xffffffffu, sm, mask), __shfl_xor_sync(0xffffffffu, sq, mask), n_half);
+          m[i] = km;
+          q[i] = kq;
+        }
+      }
+      half >>= 1;
+    } else {
+      chan_merge(m[0], q[0], __shfl_xor_sync(0xffffffffu, m[0], mask), __shfl_xor_sync(0xffffffffu, q[0], mask), n_half);
+    }
+    n_half *= 2.f;
+  }
+}
+template <int R>
+__device__ __forceinline__ int stat_row(int lane) {  // which of the R rows a lane holds after stat_reduce_scatter
+  return R == 8 ? (lane >> 2) : (R == 4 ? (lane >> 3) : (R == 2 ? (lane >> 4) : 0));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* o) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[2 * k] = __uint_as_float(w[k] << 16);
+    o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+  return u;
+}
+template <int N>
+__device__ __forceinline__ void local_stat(const float (&v)[N], float& m, float& q) {
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < N; ++e) s += v[e];
+  m = s * (1.f / N);
+  q = 0.f;
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    const float c = v[e] - m;
+    q = fmaf(c, c, q);
+  }
+}
+__device__ __forceinline__ void load8f(const float* p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(128) layernorm_cols_kernel(const fdm_norm_args a) {
+  constexpr int TPR = D / 8;     // threads per row
+  constexpr int WPR = TPR / 32;  // warps per row: 4 (d = 1024) or 2 (d = 512)
+  constexpr int RPP = 128 / TPR; // rows per pass of the CTA
+  __shared__ float2 st[R][RPP][WPR];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int sub = tid / TPR, ct = tid % TPR, wr = ct >> 5;
+  const int col0 = ct * 8;
+  const int64_t row_base = static_cast<int64_t>(blockIdx.x) * (R * RPP) + sub;
+  const int64_t last = a.rows - 1;
+  pdl_trigger();
+  float g1[8], b1[8];  // weights: independent of the previous kernel, so these loads overlap its tail
+  load8f(a.g1 + col0, g1);
+  load8f(a.b1 + col0, b1);
+  pdl_wait();
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  uint4 xr[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) xr[i] = *reinterpret_cast<const uint4*>(xp + min(row_base + i * RPP, last) * a.ldx + col0);
+  float m[R], q[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    float v[8];
+    unpack8(xr[i], v);
+    local_stat<8>(v, m[i], q[i]);
+  }
+  stat_reduce_scatter<R>(m, q, lane);
+  if ((lane & (32 / R - 1)) == 0) st[stat_row<R>(lane)][sub][wr] = make_float2(m[0], q[0]);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    float mean = 0.f, M2 = 0.f, pm[WPR];
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) {
+      const float2 p = st[i][sub][w];
+      pm[w] = p.x;
+      mean += p.x;
+      M2 += p.y;
+    }
+    mean *= 1.f / WPR;
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) M2 = fmaf((pm[w] - mean) * (pm[w] - mean), 256.f, M2);
+    const float rstd = 1.f / sqrtf(M2 * (1.f / D) + a.eps), nmr = -mean * rstd;
+    float v[8];
+    unpack8(xr[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(fmaf(v[e], rstd, nmr), g1[e], b1[e]);
+    const int64_t row = row_base + i * RPP;
+    if (row <= last) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + col0) = pack8(v);
+  }
+}
+
+// fused pair: out = LN(LN(x; g1, b1) + r2[row % r2_rows] + vec2[*vec_index_dev]; g2, b2), one warp per row
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args a, const int rows_per_cta) {
+  constexpr int NCH = D / 256;  // 16-byte chunks per lane: chunk k covers columns (32 k + lane) * 8 ...
+  constexpr int EPL = NCH * 8;
+  __shared__ float4 sp[4][D / 4];  // gamma1, beta1 + time row, gamma2, beta2
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  for (int i = tid; i < D / 4; i += 256) {
+    sp[0][i] = __ldg(reinterpret_cast<const float4*>(a.g1) + i);
+    sp[2][i] = __ldg(reinterpret_cast<const float4*>(a.g2) + i);
+    sp[3][i] = __ldg(reinterpret_cast<const float4*>(a.b2) + i);
+  }
+  pdl_wait();
+  {
+    const float4* vec = reinterpret_cast<const float4*>(a.vec2 + static_cast<int64_t>(*a.vec_index_dev) * D);
+    for (int i = tid; i < D / 4; i += 256) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(a.b1) + i), t = __ldg(vec + i);
+      sp[1][i] = make_float4(b.x + t.x, b.y + t.y, b.z + t.z, b.w + t.w);
+    }
+  }
+  __syncthreads();
+  const int64_t row_end = min(a.rows, (static_cast<int64_t>(blockIdx.x) + 1) * rows_per_cta);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(a.x);
+  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.r2);
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * rows_per_cta + warp; row < row_end; row += 8) {
+    const int64_t rr = a.r2_rows > 0 ? (row < a.r2_rows ? row : (row < 2 * a.r2_rows ? row - a.r2_rows : row % a.r2_rows)) : row;
+    uint4 xr[NCH], cr[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) xr[k] = *reinterpret_cast<const uint4*>(xp + row * a.ldx + (32 * k + lane) * 8);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cr[k] = *reinterpret_cast<const uint4*>(rp + rr * a.ldr2 + (32 * k + lane) * 8);
+    float v[EPL];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) unpack8(xr[k], v + 8 * k);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      float m, q;
+      local_stat<EPL>(v, m, q);
+      float n_half = 0.5f * EPL;
+#pragma unroll
+      for (int mask = 16; mask >= 1; mask >>= 1) {
+        chan_merge(m, q, __shfl_xor_sync(0xffffffffu, m, mask), __shfl_xor_sync(0xffffffffu, q, mask), n_half);
+        n_half *= 2.f;
+      }
+      const float rstd = 1.f / sqrtf(q * (1.f / D) + a.eps), nmr = -m * rstd;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 g = sp[2 * pass][(32 * k + lane) * 2 + h], b = sp[2 * pass + 1][(32 * k + lane) * 2 + h];
+          float* o = v + 8 * k + 4 * h;
+          o[0] = fmaf(fmaf(o[0], rstd, nmr), g.x, b.x);
+          o[1] = fmaf(fmaf(o[1], rstd, nmr), g.y, b.y);
+          o[2] = fmaf(fmaf(o[2], rstd, nmr), g.z, b.z);
+          o[3] = fmaf(fmaf(o[3], rstd, nmr), g.w, b.w);
+        }
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          float c[8];
+          unpack8(cr[k], c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 * k + e] += c[e];
+        }
+      }
+    }
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) *reinterpret_cast<uint4*>(op + (32 * k + lane) * 8) = pack8(v + 8 * k);
+  }
+}
+
+template <int D>
+bool launch_hot_ln(const fdm_norm_args& a, bool pair, cudaStream_t s) {
+  if (pair) {
+    // ~3 CTAs of 8 warps per SM, each staging the 16 KB (d = 1024) of parameters once for its share of the rows
+    const int64_t ctas = 3 * static_cast<int64_t>(fdm_sm_count());
+    int64_t per = ceil_div64(a.rows, ctas);
+    per = (per + 7) / 8 * 8;
+    const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, per));
+    return fdm_launch_pdl(layernorm_pair_kernel<D>, dim3(grid), dim3(256), 0, s, 1, a, static_cast<int>(per)) == cudaSuccess;
+  }
+  constexpr int R = 4;
+  const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, R * (128 * 8 / D)));
+  return fdm_launch_pdl(layernorm_cols_kernel<D, R>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+}
+// bf16 plain / fused-pair LayerNorm of the denoiser step. FDM_B200_LN_HOT: 0 = warp-per-two-rows kernel for both,
+// 1 = new plain kernel only, 2 = both (default)
+bool try_hot_ln(const fdm_norm_args& a, cudaStream_t s) {
+  static const int mode = [] { const char* e = getenv("FDM_B200_LN_HOT"); return e ? atoi(e) : 2; }();
+  if (mode <= 0 || a.x_dtype != FDM_BF16 || a.r1 || a.act1 != FDM_ACT_NONE || !a.g1) return false;
+  const bool plain = !a.g2, pair = a.g2 && a.r2 && a.vec2;
+  if (!(plain || (pair && mode >= 2))) return false;
+  if (a.d == 1024) return launch_hot_ln<1024>(a, pair, s);
+  if (a.d == 512) return launch_hot_ln<512>(a, pair, s);
+  return false;
+}
+
 // block = 32 channels x 8 time-lanes; grid = (C/32, B)
 __global__ void __launch_bounds__(256) leaky_instnorm_kernel(const void* x, int x_dtype, void* out, int out_dtype, int T,
                                                              int64_t t_stride, int64_t out_t_stride, int C, float slope,
@@ -354,6 +592,10 @@ extern "C" int fdm_layernorm(const fdm_norm_args* args, void* stream) {
                          al16(a.g1, 0, 4) && al16(a.b1, 0, 4) && al16(a.g2, 0, 4) && al16(a.b2, 0, 4) && al16(a.vec2, 0, 4);
     if (same && aligned && !a.out2 && (a.act1 == FDM_ACT_NONE || a.act1 == FDM_ACT_GELU_ERF) && (a.d == 512 || a.d == 1024)) {
       cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      if (try_hot_ln(a, st)) {
+        FDM_CHECK_LAUNCH();
+        return 0;
+      }
       const bool ok = a.x_dtype == FDM_BF16 ? try_fast_ln<__nv_bfloat16>(a, st) : try_fast_ln<float>(a, st);
       if (ok) {
         FDM_CHECK_LAUNCH();

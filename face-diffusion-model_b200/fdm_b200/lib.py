@@ -104,6 +104,38 @@ def load() -> C.CDLL:
     return _lib
 
 
+class _NullRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class _NvtxRange:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
+NVTX = os.environ.get("FDM_B200_NVTX", "0") == "1"
+_NULL_RANGE = _NullRange()
+
+
+def nvtx_range(name: str):
+    """NVTX range around one stage of the sampling job (audio encoder, prepare, sampling loop, tail, quantise, decode,
+    gather) when FDM_B200_NVTX=1: `ncu --nvtx --nvtx-include "fdm/decode/"` then profiles exactly that stage. Off by
+    default (a no-op context manager)."""
+    return _NvtxRange("fdm/" + name) if NVTX else _NULL_RANGE
+
+
 def require_device() -> C.CDLL:
     """Library + an sm_100 device, or raise."""
     global _device_checked

@@ -191,7 +191,8 @@ class FDMBase(nn.Module):
             self.audio_encoder.precision = mode
         wkey = self._audio_weights_key()
         if c is None or not self._same(c[0], (audio,)) or c[1] != (mode, wkey):
-            hidden = self.audio_encoder(audio).last_hidden_state
+            with lib.nvtx_range("audio_encoder"):
+                hidden = self.audio_encoder(audio).last_hidden_state
             assert hidden.dtype == (torch.bfloat16 if mode == "bf16" else torch.float32)
             c = (self._ident((audio,)), (mode, self._audio_weights_key()), hidden.contiguous())
             self.__dict__["_audio_cache"] = c
@@ -231,7 +232,8 @@ class FDMBase(nn.Module):
         if k is None or k[1] != meta or not self._same(k[0], (audio, id_one_hot, emo_one_hot)) or eng.B == 0:
             if hidden.dtype != eng.dtype:  # split-bf16 audio features feeding the bf16 step engine
                 hidden = lib.cast(hidden, torch.empty_like(hidden, dtype=eng.dtype))
-            eng.prepare(hidden, n_frames, id_one_hot, emo_one_hot, guidance)
+            with lib.nvtx_range("prepare_tail" if tail else "prepare"):
+                eng.prepare(hidden, n_frames, id_one_hot, emo_one_hot, guidance)
             self.__dict__[slot] = (self._ident((audio, id_one_hot, emo_one_hot)), meta)
         return eng
 
@@ -429,9 +431,10 @@ class GaussianDiffusionBase(nn.Module):
         x_T = self._initial_latent(tuple(shape), device, seed) if x_T is None else x_T.to(device, torch.float32)
         eng = fdm.prepare(audio, shape[1] // P.fq, idh, emo, guidance=gcond)
         sampler = SamplerEngine(eng, self.posterior_mean_coef1, self.posterior_mean_coef2, self._sigma_table(), level)
-        out = sampler.run(x_T, steps, noise=self.noise_source, seed=seed, clip_index0=self.clip_index0,
-                          graph=self.use_cuda_graph, tap=tap, time_steps=getattr(self, "time_steps", False),
-                          tail=self._tail(fdm, audio, shape[1] // P.fq, idh, emo, gcond, len(steps)))
+        tail = self._tail(fdm, audio, shape[1] // P.fq, idh, emo, gcond, len(steps))
+        with lib.nvtx_range("sampling_loop"):
+            out = sampler.run(x_T, steps, noise=self.noise_source, seed=seed, clip_index0=self.clip_index0,
+                              graph=self.use_cuda_graph, tap=tap, time_steps=getattr(self, "time_steps", False), tail=tail)
         self.__dict__["_last_sampler"] = sampler
         return out
 
@@ -464,9 +467,10 @@ class GaussianDiffusionBase(nn.Module):
         x_T = self._initial_latent(shape, device, self._call_seed()) if x_T is None else x_T.to(device, torch.float32)
         eng = fdm.prepare(audio, shape[1] // P.fq, idh, emo, guidance=gcond)
         sampler = SamplerEngine(eng, self.posterior_mean_coef1, self.posterior_mean_coef2, self._sigma_table(), level)
-        out = sampler.run(x_T, [p[0] for p in pairs], graph=self.use_cuda_graph, tap=tap, ddim=tables,
-                          time_steps=getattr(self, "time_steps", False),
-                          tail=self._tail(fdm, audio, shape[1] // P.fq, idh, emo, gcond, len(pairs)))
+        tail = self._tail(fdm, audio, shape[1] // P.fq, idh, emo, gcond, len(pairs))
+        with lib.nvtx_range("ddim_loop"):
+            out = sampler.run(x_T, [p[0] for p in pairs], graph=self.use_cuda_graph, tap=tap, ddim=tables,
+                              time_steps=getattr(self, "time_steps", False), tail=tail)
         self.__dict__["_last_sampler"] = sampler
         return out
 
@@ -612,8 +616,9 @@ class VQAutoEncoderBase(nn.Module):
         if self.emotion_sliced and one_hot is None:
             raise TypeError("quant() of the emotion EVQ-VAE needs the emotion one-hot")
         z = x.detach().float().contiguous()
-        idx, zq, zr = quantize(z, self.quantize.embedding.weight, self.n_local if self.emotion_sliced else self.args.n_embed,
-                               one_hot if self.emotion_sliced else None, want_bdl=True, want_rows=True)
+        with lib.nvtx_range("quantize"):
+            idx, zq, zr = quantize(z, self.quantize.embedding.weight, self.n_local if self.emotion_sliced else self.args.n_embed,
+                                   one_hot if self.emotion_sliced else None, want_bdl=True, want_rows=True)
         # decode() shortcut: the row layout the quantiser kernel already produced travels WITH the returned tensor
         # (an attribute of that tensor object, valid for its current version), never keyed on an address
         zq._fdm_rows = (zr, zq._version)
@@ -646,4 +651,5 @@ class VQAutoEncoderBase(nn.Module):
         rows = rows.view(B, T, a.face_quan_num * D)
         if clips is not None:
             rows = rows[clips[0]:clips[1]]
-        return self.engine().decode_rows(rows, out=out)
+        with lib.nvtx_range("decode"):
+            return self.engine().decode_rows(rows, out=out)

@@ -11,6 +11,8 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from . import lib
+
 
 def shard_range(n_clips: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, equal-count split (the all-gather needs equal counts): returns (first clip, clip count)."""
@@ -28,7 +30,8 @@ def gather_clips(local: torch.Tensor, group=None, out: Optional[torch.Tensor] = 
     local = local.contiguous()
     if out is None:
         out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out.view(-1), local.view(-1), group=group)
+    with lib.nvtx_range("all_gather"):
+        dist.all_gather_into_tensor(out.view(-1), local.view(-1), group=group)
     return out
 
 

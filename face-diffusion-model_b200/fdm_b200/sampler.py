@@ -175,8 +175,12 @@ class SamplerEngine:
                     tap(t, x0.clone())
                 step_body()  # (recomputes the denoiser when tapping: taps are a debugging aid)
         for t in tail_steps:  # high-precision tail: eager launches on the same loop state, schedule cursor and seed
+            if lib.NVTX:
+                torch.cuda.nvtx.range_push("fdm/tail_step")
             feed_noise(t)
             if tap is not None:
                 tap(t, tail_den.denoise(x.view(B * T, d), t_dev).clone())
             step_body(hi=True)
+            if lib.NVTX:
+                torch.cuda.nvtx.range_pop()
         return x.view(x_T.shape).clone()  # the loop state buffer is reused by the next call

@@ -78,6 +78,37 @@ def test_gemm_bf16_out_with_bf16_residual_tma_path(cuda_dev, M, N, K):
     assert torch.equal(out, x)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 512), (130, 200, 64), (128, 64, 128), (6000, 1024, 2048), (5003, 1288, 320),
+                                   (12672, 1024, 1024), (25344, 1024, 2048), (4099, 1280, 192), (700, 72, 64)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_bf16_residual_through_mma(cuda_dev, M, N, K, out_dtype):
+    """bf16 residual, no activation (out-projection / FFN2 of the denoiser layers), both residual paths: the TMA-residual
+    epilogue and (FDM_B200_GEMM_RESMMA=1, set by tests/conftest.py for a second pass of this file's GEMM tests in
+    tools/sanitize.sh / the A-B scripts) the residual tile accumulated by the tensor core as identity k-blocks. All three
+    tile kernels, M / N / K tails, fp32 and bf16 outputs, the in-place form x = x + f(x)."""
+    from fdm_b200 import lib
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    ld = (N + 7) // 8 * 8  # residual rows 16-byte aligned (what the TMA path needs); N itself may be ragged
+    res_buf = (3 * torch.randn(M, ld, generator=g)).to(cuda_dev).bfloat16()
+    res = res_buf[:, :N]
+    ref = a.float() @ w.float().t() + bias + res.float()
+    out = torch.full((M, N), float("nan"), device=cuda_dev, dtype=out_dtype)
+    lib.gemm(a, w, out, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < (6e-3 if out_dtype == torch.bfloat16 else 2e-5)
+    err = (out.float() - ref).abs().max().item()
+    assert err < (0.15 if out_dtype == torch.bfloat16 else 2e-3), err
+    if out_dtype == torch.bfloat16:
+        x_buf = res_buf.clone()
+        lib.gemm(a, w, x_buf[:, :N], bias=bias, residual=x_buf[:, :N])  # in place
+        torch.cuda.synchronize()
+        assert torch.equal(out, x_buf[:, :N])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_gemm_implicit_conv(cuda_dev, dtype):
     """Conv1d(k=5, pad=2 replicate) and a stride-2 k=3 conv as shifted-row / overlapping-row GEMMs."""
@@ -211,6 +242,37 @@ def test_layernorm_fused(cuda_dev, d, dtype):
     o3 = torch.empty(rows, d, device=cuda_dev, dtype=dtype)
     lib.layernorm(x, o3, g1=g1, b1=b1, act1=lib.ACT_GELU_ERF)
     assert _rel(o3, F.gelu(F.layer_norm(x.float(), (d,), g1, b1))) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d", [512, 1024])
+@pytest.mark.parametrize("rows", [7, 64, 333, 2 * 198 * 3])
+@pytest.mark.parametrize("offset", [0.0, 30.0])
+def test_layernorm_hot_modes(cuda_dev, d, rows, offset):
+    """The denoiser step's two bf16 LayerNorm launches (column-owner kernel): plain norm3 and the fused pair
+    norm1 -> + cross cache (shared by the two guidance passes: r2 has rows / 2 rows) + time row -> norm2; ragged row counts,
+    and inputs with a mean of 30 standard deviations (the (mean, M2) merge must not cancel)."""
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(d + rows)
+    mk = lambda *s: torch.randn(*s, generator=g).to(cuda_dev)
+    x = (mk(rows, d) + offset).bfloat16()
+    half = rows // 2 if rows % 2 == 0 else rows
+    r2 = mk(half, d).bfloat16()
+    g1, b1, g2, b2 = 1 + 0.1 * mk(d), mk(d), 1 + 0.1 * mk(d), mk(d)
+    vec = mk(10, d)
+    idx = torch.tensor([3], dtype=torch.int32, device=cuda_dev)
+    out = torch.full((rows + 1, d), 7.0, device=cuda_dev, dtype=torch.bfloat16)
+    lib.layernorm(x, out[:rows], g1=g1, b1=b1)
+    ref = F.layer_norm(x.float(), (d,), g1, b1)
+    assert (out[:rows].float() - ref).abs().max() < 2e-2 * max(1.0, float(ref.abs().max()))
+    assert _rel(out[:rows], ref) < 4e-3
+    assert float(out[rows].float().min()) == 7.0  # nothing written past the last row
+    out.fill_(7.0)
+    lib.layernorm(x, out[:rows], g1=g1, b1=b1, r2=r2, vec2=vec, vec_index_dev=idx, g2=g2, b2=b2)
+    ref2 = F.layer_norm(ref + r2.float().repeat(rows // half, 1) + vec[3], (d,), g2, b2)
+    assert _rel(out[:rows], ref2) < 4e-3
+    assert float(out[rows].float().min()) == 7.0
 
 
 def _alibi_mask(H, T, period):
