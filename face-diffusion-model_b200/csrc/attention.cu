@@ -7,6 +7,7 @@
 int fdm_attention_mma_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);  // attention_mma.cu
 int fdm_attention_tc_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);   // attention_tc.cu
 int fdm_attention_tc2_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);  // attention_tc2.cu
+int fdm_attention_tc3_try(const fdm_attn_args& a, cudaStream_t stream, bool* handled);  // attention_tc3.cu
 
 namespace {
 
@@ -161,6 +162,8 @@ extern "C" int fdm_self_attention(const fdm_attn_args* args, void* stream) {
     int rc = fdm_attention_tc2_try(a, s, &handled);  // tcgen05/TMEM kernel, 16 softmax warps: head dim 128, T <= 208, causal or unmasked
     if (rc != 0 || handled) return rc;
     rc = fdm_attention_tc_try(a, s, &handled);       // first-generation tcgen05 kernel (FDM_B200_ATTN_TC=1)
+    if (rc != 0 || handled) return rc;
+    rc = fdm_attention_tc3_try(a, s, &handled);      // general tcgen05 kernel: head dim 64 / 128 / 256, key blocks of 64, two-pass softmax
     if (rc != 0 || handled) return rc;
     rc = fdm_attention_mma_try(a, s, &handled);      // mma.sync kernel: head dim 64 / 128, any bias mode
     if (rc != 0 || handled) return rc;

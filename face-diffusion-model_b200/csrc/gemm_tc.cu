@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -815,6 +816,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // IDENT_COPIES x (64 x 64 bf16 identity) (the B operand of the residual k-blocks), per device, created by fdm_device_info()
 void* g_identity[64] = {nullptr};
+int g_resmma = -1;  // -1: read FDM_B200_GEMM_RESMMA on first use; fdm_gemm_set_option overrides
 
 template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA>
 int launch_impl(const fdm_gemm_args& a, const Epilogue& ep_in, cudaStream_t stream) {
@@ -881,8 +883,11 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   if (ep.a_ln || ep.res_ln || ep.stats_out) return launch_impl<BLOCK_N, CG, true, false, false>(a, ep, stream);
   // bf16 residual without an activation: optionally added by the tensor core (FDM_B200_GEMM_RESMMA=1; default: the
   // TMA-residual epilogue)
-  static const bool resmma = [] { const char* e = getenv("FDM_B200_GEMM_RESMMA"); return e && e[0] == '1'; }();
-  if (resmma && a.residual && a.res_dtype == FDM_BF16 && a.act == FDM_ACT_NONE && aligned16(a.residual) && (a.ldr * 2) % 16 == 0)
+  if (g_resmma < 0) {
+    const char* e = getenv("FDM_B200_GEMM_RESMMA");
+    g_resmma = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_resmma == 1 && a.residual && a.res_dtype == FDM_BF16 && a.act == FDM_ACT_NONE && aligned16(a.residual) && (a.ldr * 2) % 16 == 0)
     return launch_impl<BLOCK_N, CG, false, false, true>(a, ep, stream);
   return launch_impl<BLOCK_N, CG, false, false, false>(a, ep, stream);
 }
@@ -908,6 +913,16 @@ int fdm_gemm_init_device() {  // not during stream capture: allocates
     FDM_CHECK_CUDA(cudaMemcpy(static_cast<uint8_t*>(p) + sizeof(host) * c, host, sizeof(host), cudaMemcpyHostToDevice));
   g_identity[dev] = p;
   return 0;
+}
+
+extern "C" int fdm_gemm_set_option(const char* name, int32_t value) {
+  FDM_CHECK_ARG(name != nullptr, "fdm_gemm_set_option: null name");
+  if (strcmp(name, "resmma") == 0) {
+    g_resmma = value ? 1 : 0;
+    return 0;
+  }
+  FDM_CHECK_ARG(false, "fdm_gemm_set_option: unknown option '%s'", name);
+  return 1;
 }
 
 extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
@@ -961,8 +976,16 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   const int sms = fdm_sm_count();
   // CTA-pair kernel (256 x 256 tiles) whenever there is at least one tile per SM pair and C can go through TMA
   static const bool two_cta = [] { const char* e = getenv("FDM_B200_GEMM_2CTA"); return !(e && e[0] == '0'); }();
-  if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2)
+  if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2) {
+    // 256 x 128 tiles when the 256 x 256 schedule leaves the last wave mostly empty (N = 1024 at M = 25344: 396 tiles on 74
+    // CTA pairs = 5.35 waves, 89 % of six; 792 half-width tiles fill 97 % of eleven). FDM_B200_GEMM_BN128: 0 never, 1 always.
+    static const int bn128 = [] { const char* e = getenv("FDM_B200_GEMM_BN128"); return e ? atoi(e) : -1; }();
+    const int64_t pairs = sms / 2, t256 = ceil_div64(a.M, 256) * ceil_div64(a.N, 256), t128 = ceil_div64(a.M, 256) * ceil_div64(a.N, 128);
+    const double e256 = static_cast<double>(t256) / (pairs * ceil_div64(t256, pairs));
+    const double e128 = static_cast<double>(t128) / (pairs * ceil_div64(t128, pairs));
+    if (bn128 == 1 || (bn128 < 0 && e256 < 0.92 && e128 > e256 + 0.05)) return launch<128, 2>(a, ep, s);
     return launch<256, 2>(a, ep, s);
+  }
   if (a.N >= 128 && m_tiles * ceil_div64(a.N, 128) >= sms) return launch<128>(a, ep, s);
   if (a.N > 64 && a.N % 64 != 0 && a.N >= 128) return launch<128>(a, ep, s);
   return launch<64>(a, ep, s);

@@ -152,6 +152,27 @@ __global__ void __launch_bounds__(1024) audio_normalize_pad_kernel(const float* 
   for (int64_t i = threadIdx.x; i < Lout; i += blockDim.x) y[i] = i < L ? (x[i] - mean) * rstd : 0.f;
 }
 
+// Polyphase FIR resampler (scipy.signal.resample_poly / upfirdn semantics): out[m] = sum_k taps[k] * xup[(m + pre) * down - k]
+// with xup the input zero-stuffed by `up`. One thread per output sample; only the taps that meet a non-zero sample are visited
+// (k = k0 + up * q), ~ n_taps / up multiply-adds per output. The demo path's librosa.load(sr=16000) resampling
+// (demo/demo_3d_mead.py:83) on the GPU; the filter itself is designed on the host (fdm_b200/frontend.py).
+__global__ void __launch_bounds__(256) resample_poly_kernel(const float* __restrict__ in, int64_t L_in, float* __restrict__ out,
+                                                            int64_t L_out, const float* __restrict__ taps, int n_taps, int up, int down,
+                                                            int64_t pre) {
+  const int64_t m = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= L_out) return;
+  const float* x = in + static_cast<int64_t>(blockIdx.y) * L_in;
+  const int64_t p = (m + pre) * down;
+  const int k0 = static_cast<int>(p % up);
+  int64_t i = p / up;  // input sample that meets taps[k0]
+  float acc = 0.f;
+  for (int k = k0; k < n_taps; k += up, --i) {
+    if (i < 0) break;
+    if (i < L_in) acc = fmaf(taps[k], x[i], acc);
+  }
+  out[static_cast<int64_t>(blockIdx.y) * L_out + m] = acc;
+}
+
 // One CTA per frame: reduce over a vertex subset the squared L2 distance between prediction and ground truth
 // (metric/metric.py:115-138: per-frame max for LVE / FVE / all-vertex error, per-frame mean for EME).
 __global__ void __launch_bounds__(256) vertex_error_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int64_t V,
@@ -258,6 +279,18 @@ extern "C" int fdm_cast_rows(const float* src, int64_t ld_src, void* dst, int32_
 extern "C" int fdm_audio_normalize_pad(const float* audio, int64_t B, int64_t L, float* out, int64_t Lout, float eps, void* stream) {
   FDM_CHECK_ARG(audio && out && B > 0 && L > 0 && Lout >= L, "fdm_audio_normalize_pad: bad arguments");
   audio_normalize_pad_kernel<<<static_cast<unsigned>(B), 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(audio, L, out, Lout, eps);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_resample_poly(const float* audio, int64_t B, int64_t L_in, float* out, int64_t L_out, const float* taps,
+                                 int64_t n_taps, int64_t up, int64_t down, int64_t pre, void* stream) {
+  FDM_CHECK_ARG(audio && out && taps && B > 0 && B <= 65535 && L_in > 0 && L_out > 0 && n_taps > 0 && n_taps < (1ll << 30) && up > 0 &&
+                    down > 0 && up < (1 << 20) && down < (1 << 20) && pre >= 0,
+                "fdm_resample_poly: bad arguments");
+  dim3 grid(static_cast<unsigned>(ceil_div64(L_out, 256)), static_cast<unsigned>(B));
+  resample_poly_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(audio, L_in, out, L_out, taps, static_cast<int>(n_taps),
+                                                                                static_cast<int>(up), static_cast<int>(down), pre);
   FDM_CHECK_LAUNCH();
   return 0;
 }

@@ -59,6 +59,7 @@ EXPORTS = {
     "fdm_last_error": (C.c_char_p, []),
     "fdm_device_info": (C.c_int, [C.POINTER(_i32)] * 3),
     "fdm_abi_version": (C.c_int, []),
+    "fdm_gemm_set_option": (C.c_int, [C.c_char_p, _i32]),
     "fdm_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "fdm_ln_stats_finalize": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _vp, _vp]),
@@ -75,6 +76,7 @@ EXPORTS = {
     "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "fdm_cast_rows": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "fdm_audio_normalize_pad": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _f32, _vp]),
+    "fdm_resample_poly": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
     "fdm_vertex_error": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _vp]),
     "fdm_transpose_bcl_to_blc": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp]),
     "fdm_pad_time": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
@@ -268,6 +270,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     return out
 
 
+def gemm_set_option(name: str, value: int) -> None:
+    """Process-wide kernel-selection switch of fdm_gemm_bf16 (see include/fdm_b200.h), e.g. ("resmma", 1)."""
+    _check(load().fdm_gemm_set_option(name.encode(), int(value)))
+
+
 def ln_stats_finalize(partials: torch.Tensor, M: int, parts: int, d: int, out: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """(mean, rstd) per row [M, 2] from the [M, parts, 2] partial statistics written by gemm(..., stats_out=...)."""
     assert partials.dtype == torch.float32 and out.dtype == torch.float32 and out.numel() >= 2 * M
@@ -435,6 +442,17 @@ def audio_normalize_pad(audio: torch.Tensor, pad_samples: int = 0, eps: float = 
     B, L = audio.shape
     out = torch.empty(B, L + pad_samples, device=audio.device, dtype=torch.float32)
     _check(require_device().fdm_audio_normalize_pad(_ptr(audio), B, L, _ptr(out), L + pad_samples, eps, _stream()))
+    _launched()
+    return out
+
+
+def resample_poly(audio: torch.Tensor, taps: torch.Tensor, up: int, down: int, pre: int, n_out: int) -> torch.Tensor:
+    """Polyphase FIR resampling on device (scipy.signal.resample_poly semantics; see fdm_resample_poly). audio (B, L) f32."""
+    assert audio.dtype == torch.float32 and audio.dim() == 2 and audio.is_contiguous()
+    assert taps.dtype == torch.float32 and taps.is_contiguous() and taps.device == audio.device
+    B, L = audio.shape
+    out = torch.empty(B, n_out, device=audio.device, dtype=torch.float32)
+    _check(require_device().fdm_resample_poly(_ptr(audio), B, L, _ptr(out), n_out, _ptr(taps), taps.numel(), up, down, pre, _stream()))
     _launched()
     return out
 

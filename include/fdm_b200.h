@@ -90,6 +90,10 @@ typedef struct fdm_gemm_args {
   const void* W_lo;
 } fdm_gemm_args;
 
+/* Kernel-selection switches of fdm_gemm_bf16 (process-wide; results are identical up to fp32 summation order):
+ *   "resmma" = 1: a bf16 residual of a GEMM without activation is accumulated by the tensor core (identity k-blocks appended
+ *                 to the K loop) instead of being added in the epilogue; 0 (default, or env FDM_B200_GEMM_RESMMA) = epilogue. */
+int fdm_gemm_set_option(const char* name, int32_t value);
 /* TMA-fed tcgen05/TMEM GEMM, bf16 operands, fp32 accumulation. */
 int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream);
 /* fp32 FFMA GEMM (deterministic k order) — the "fp32 mode" used for the 1e-4 parity runs. */
@@ -241,6 +245,12 @@ int fdm_cast_rows(const float* src, int64_t ld_src, void* dst, int32_t dst_dtype
  * samples (the demos append one second). audio [B, L] f32 -> out [B, Lout] f32. */
 int fdm_audio_normalize_pad(const float* audio, int64_t B, int64_t L, float* out, int64_t Lout, float eps,
                             void* stream);
+/* Polyphase FIR resampling with scipy.signal.resample_poly semantics, B clips of L_in samples -> L_out samples:
+ * out[m] = sum_k taps[k] * xup[(m + pre) * down - k], xup = input zero-stuffed by `up`. The taps (low-pass design, already
+ * scaled by `up` and front-padded) and `pre` come from the host (fdm_b200/frontend.py: resample). The demo path's
+ * librosa.load(path, sr=16000) step (demo/demo_3d_mead.py:83), SURVEY section 8(f) item 2. */
+int fdm_resample_poly(const float* audio, int64_t B, int64_t L_in, float* out, int64_t L_out, const float* taps,
+                      int64_t n_taps, int64_t up, int64_t down, int64_t pre, void* stream);
 /* Vertex-error metrics of metric/metric.py:115-138 on device: for every frame, reduce over the vertices
  * vertex_idx[0..n_idx) (NULL: all V vertices) the squared L2 distance between pred and gt ([frames, V, 3] f32;
  * gt == NULL compares against zeros): mode 0 = max (LVE / FVE / all-vertex error), mode 1 = mean (EME).

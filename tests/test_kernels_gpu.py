@@ -81,12 +81,13 @@ def test_gemm_bf16_out_with_bf16_residual_tma_path(cuda_dev, M, N, K):
 @pytest.mark.parametrize("M,N,K", [(300, 1024, 512), (130, 200, 64), (128, 64, 128), (6000, 1024, 2048), (5003, 1288, 320),
                                    (12672, 1024, 1024), (25344, 1024, 2048), (4099, 1280, 192), (700, 72, 64)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
-def test_gemm_bf16_residual_through_mma(cuda_dev, M, N, K, out_dtype):
+@pytest.mark.parametrize("resmma", [0, 1])
+def test_gemm_bf16_residual_through_mma(cuda_dev, M, N, K, out_dtype, resmma):
     """bf16 residual, no activation (out-projection / FFN2 of the denoiser layers), both residual paths: the TMA-residual
-    epilogue and (FDM_B200_GEMM_RESMMA=1, set by tests/conftest.py for a second pass of this file's GEMM tests in
-    tools/sanitize.sh / the A-B scripts) the residual tile accumulated by the tensor core as identity k-blocks. All three
-    tile kernels, M / N / K tails, fp32 and bf16 outputs, the in-place form x = x + f(x)."""
+    epilogue (resmma = 0) and the residual tile accumulated by the tensor core as identity k-blocks (resmma = 1,
+    fdm_gemm_set_option). All three tile kernels, M / N / K tails, fp32 and bf16 outputs, the in-place form x = x + f(x)."""
     from fdm_b200 import lib
+    lib.gemm_set_option("resmma", resmma)
     g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K)
     a = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
     w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev).bfloat16()
@@ -107,6 +108,7 @@ def test_gemm_bf16_residual_through_mma(cuda_dev, M, N, K, out_dtype):
         lib.gemm(a, w, x_buf[:, :N], bias=bias, residual=x_buf[:, :N])  # in place
         torch.cuda.synchronize()
         assert torch.equal(out, x_buf[:, :N])
+    lib.gemm_set_option("resmma", 0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -315,6 +317,41 @@ def test_attention(cuda_dev, H, dh, T, causal, dtype):
     ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
     got = out.view(B, t_stride, d)[:, :T]
     assert _rel(got, ref) < (2e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("H,dh,T,causal,B", [(4, 256, 149, True, 64), (4, 256, 192, True, 48), (4, 256, 298, True, 30),
+                                             (16, 64, 498, False, 12), (12, 64, 299, False, 16), (16, 64, 199, False, 20),
+                                             (8, 128, 498, True, 24), (8, 128, 512, True, 20), (8, 128, 300, False, 24),
+                                             (8, 128, 498, False, 20), (2, 64, 65, True, 100), (1, 64, 1, False, 200),
+                                             (3, 128, 64, True, 70), (4, 256, 33, False, 50)])
+def test_attention_tcgen05_general(cuda_dev, H, dh, T, causal, B):
+    """attention_tc3.cu: head dim 64 / 128 / 256, key blocks of 64 with the exact two-pass softmax. More (sequence, head,
+    query tile) items than SMs, so every persistent CTA runs several items back to back (ring / barrier parities across
+    items), ragged last key block and query tile, T = 1, the BIWI (4 x 256, T = 149), HuBERT (16 x 64, N = 498), wav2vec2
+    (12 x 64, N = 299) and 10 s VOCASET (8 x 128, T = 498) shapes. Rows between the sequences must stay untouched."""
+    from fdm_b200 import lib
+    d = H * dh
+    t_stride = T + 3
+    g = torch.Generator(device="cpu").manual_seed(T + dh)
+    qkv = torch.randn(B, t_stride, 3 * d, generator=g).to(cuda_dev).bfloat16()
+    out = torch.full((B * t_stride, d), 3.0, device=cuda_dev, dtype=torch.bfloat16)
+    rows = qkv.view(B * t_stride, 3 * d)
+    slopes = None
+    scale = 1.0 / math.sqrt(dh)
+    bias = torch.zeros(H, T, T)
+    if causal:
+        slopes, bias = _alibi_mask(H, T, 25)
+        slopes = slopes.to(cuda_dev)
+    lib.self_attention(rows[:, 0:], rows[:, d:], rows[:, 2 * d:], out, B, T, t_stride, H, dh, scale, slopes=slopes, period=25)
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, t_stride, H, dh)[:, :T].permute(0, 2, 1, 3) for t in qkv.split(d, dim=-1)]
+    s = (q @ k.transpose(-1, -2)) * scale + bias.to(cuda_dev)
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
+    got = out.view(B, t_stride, d)
+    assert torch.isfinite(got.float()).all()
+    assert _rel(got[:, :T], ref) < 1e-2
+    assert (got[:, :T].float() - ref).abs().max() < 0.06
+    assert bool((got[:, T:] == 3.0).all())  # padding rows between the sequences are not written
 
 
 def test_ddpm_step_bit_exact(cuda_dev):
