@@ -5,17 +5,20 @@
 //   * the EVQ-VAE transformer (8 x 128, unmasked, models/lib/base_models.py:138-174) and the VOCASET FDM at 10 s (T = 498).
 //
 // Work item = (sequence, head, 128-row query tile), persistent CTAs, heaviest (latest causal) tiles first. Keys stream
-// through a shared-memory ring in blocks of 64. Exact two-pass softmax, no rescaling of the accumulator:
-//   pass 1   S_b = Q K_b^T (tcgen05.mma into a double-buffered 64-column TMEM tile) -> row maximum of the raw scores
-//   pass 2   S_b again -> P_b = exp2(S_b * scale + bias - max) as bf16 in the K-major swizzled A-operand layout (double
-//            buffered) -> O += P_b V_b (V_b as an MN-major B operand) ; O / rowsum -> bf16 -> TMA store
+// through a shared-memory ring in blocks of 64; a score tile spans ST blocks (128 keys for head dim <= 128, 64 for head dim
+// 256 where shared memory only holds 64-key P tiles). Exact two-pass softmax, no rescaling of the accumulator:
+//   pass 1   S_t = Q K_t^T (tcgen05.mma into a double-buffered TMEM tile) -> row maximum of the raw scores
+//   pass 2   S_t again -> P_t = exp2(S_t * scale + bias - max) as bf16 in the K-major swizzled A-operand layout (double
+//            buffered) -> O += P_t V_t (V as an MN-major B operand) ; O / rowsum -> bf16 -> TMA store
 // The second Q K^T costs tensor-pipe time the kernel has to spare (the softmax warps are the bottleneck: TMEM read bandwidth
 // per lane quadrant and the MUFU pipe, see attention_tc2.cu) and keeps the arithmetic identical to the single-tile kernel:
 // the maximum is exact, so no lazy-rescale path and no data-dependent timing.
 // Warp roles (19 warps): 0 K/V producer (TMA), 1 MMA issuer, 2-17 softmax + epilogue (TMEM lane quadrant = warp % 4, four
 // threads per query row, 16 keys of a block each), 18 query loads + output stores (so the K/V ring keeps prefetching the
 // next item while an output tile drains). Every wait is an mbarrier try_wait loop with a watchdog trap.
-// TMEM: O [0, DH) | S_0 [256, 320) | S_1 [320, 384).
+// Head dim <= 128: two query buffers and the output tile staged in the (by then idle) P buffers, so an item switch costs no
+// load / store round trip; head dim 256: one 64 KB query buffer that doubles as the staging tile.
+// TMEM: O [0, DH) | S_0 [256, 256 + 64 ST) | S_1 [256 + 64 ST, 256 + 128 ST).
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -30,7 +33,7 @@ constexpr int NUM_THREADS = 64 + SM_THREADS + 32;
 constexpr int TAB_FLOATS = 640;  // bias table of the item's head: index = (t - j) + 128, t - j in [-127, 511]
 constexpr int T_MAX_CAUSAL = 512;
 constexpr int MAX_SLOTS = 8;
-enum { B_QFULL = 0, B_OFULL, B_OEMPTY, B_OUTFULL, B_SFULL, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2,
+enum { B_QFULL = 0, B_QEMPTY = 2, B_STGFREE = 4, B_OFULL, B_OEMPTY, B_OUTFULL, B_SFULL, B_SEMPTY = B_SFULL + 2, B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2,
        B_KVFULL = B_PEMPTY + 2, B_KVEMPTY = B_KVFULL + MAX_SLOTS, NUM_BARS = B_KVEMPTY + MAX_SLOTS };
 
 template <int DH>
@@ -38,9 +41,14 @@ struct Cfg3 {
   static constexpr int G = DH / 64;               // 64-column groups of the head dim
   static constexpr int Q_BYTES = 128 * DH * 2;    // query tile: G k-blocks of [128 rows][128 B]; reused as the output staging tile
   static constexpr int SLOT_BYTES = BK * DH * 2;  // one K or V block: G groups of [64 keys][128 B]
-  static constexpr int NSLOT = DH == 256 ? 3 : (DH == 128 ? 6 : 8);
-  static constexpr int P_BYTES = 128 * BK * 2;    // 16 KB
-  static constexpr int OFF_KV = Q_BYTES;
+  static constexpr int NSLOT = DH == 256 ? 3 : (DH == 128 ? 5 : 8);
+  // head dim <= 128: two query buffers (the next item's tile lands while this one computes) and the output tile is staged in
+  // the P buffers; head dim 256: one query buffer that doubles as the output staging tile (64 KB each)
+  static constexpr int QBUF = DH == 256 ? 1 : 2;
+  static constexpr int ST = DH == 256 ? 1 : 2;    // key blocks (ring slots) per score tile
+  static constexpr int KT = BK * ST;              // keys per score tile
+  static constexpr int P_BYTES = 128 * KT * 2;    // ST k-blocks of [128 rows][128 B]
+  static constexpr int OFF_KV = QBUF * Q_BYTES;
   static constexpr int OFF_P = OFF_KV + NSLOT * SLOT_BYTES;
   static constexpr int OFF_TAB = OFF_P + 2 * P_BYTES;
   static constexpr int OFF_XCH = OFF_TAB + TAB_FLOATS * 4;
@@ -48,6 +56,7 @@ struct Cfg3 {
   static constexpr int SMEM_BYTES = OFF_BAR + 8 * NUM_BARS + 16 + 1024;  // + TMEM slot + manual 1024-byte alignment
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(NSLOT <= MAX_SLOTS, "ring too deep");
+  static_assert(QBUF == 1 || Q_BYTES <= 2 * P_BYTES, "the output tile must fit the P buffers");
 };
 
 struct Ring {  // position in a ring of N single-use-per-lap buffers
@@ -87,7 +96,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < NUM_BARS; ++i) {
       // barriers the softmax warps arrive on take ONE arrival per warp (lane 0 after __syncwarp)
-      const bool sm = i == B_OEMPTY || i == B_OUTFULL || i == B_SEMPTY || i == B_SEMPTY + 1 || i == B_PFULL || i == B_PFULL + 1;
+      const bool sm = i == B_OEMPTY || i == B_OUTFULL || i == B_SEMPTY || i == B_SEMPTY + 1 || i == B_PFULL || i == B_PFULL + 1;  // (B_QEMPTY, B_STGFREE: one arrival)
       mbar_init(bar(i), sm ? SM_WARPS : 1);
     }
     fence_barrier_init();
@@ -115,7 +124,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== K/V producer: pass 1 wants K_0 .. K_{n-1}; pass 2 consumes K_0, K_1, V_0, K_2, V_1, ... , V_{n-1} =====
+      // ===== K/V producer: pass 1 wants the K blocks in order; pass 2 consumes tile by tile K(0), K(1), V(0), K(2), V(1), ... =====
       Ring r;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int seq, h, qt;
@@ -130,12 +139,13 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           r.next(C::NSLOT);
         };
         for (int b = 0; b < n; ++b) load(&tm_k, b);
-        load(&tm_k, 0);
-        for (int b = 1; b < n; ++b) {
-          load(&tm_k, b);
-          load(&tm_v, b - 1);
+        for (int b0 = 0; b0 < n; b0 += C::ST) {  // blocks [b0, b1) = one score tile
+          const int b1 = min(b0 + C::ST, n);
+          for (int b = b0; b < b1; ++b) load(&tm_k, b);
+          if (b0 > 0)
+            for (int b = b0 - C::ST; b < b0; ++b) load(&tm_v, b);
         }
-        load(&tm_v, n - 1);
+        for (int b = (n - 1) / C::ST * C::ST; b < n; ++b) load(&tm_v, b);
       }
     }
   } else if (warp == 1) {
@@ -144,20 +154,23 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, BK, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, DH, 1);
       Ring r, rs, rp;  // K/V ring, S buffers, P buffers
-      auto qk = [&]() {  // S[rs.idx] = Q K_blk^T with the block in ring slot r.idx
-        mbar_wait(bar(B_KVFULL + r.idx), r.lap, "attn_tc3 mma K");
+      uint32_t sQcur = sQ;
+      auto qk = [&](int nb) {  // S[rs.idx][:, 64 s2 ...] = Q K_blk^T for the nb blocks of a score tile (ring slots r.idx ...)
         mbar_wait(bar(B_SEMPTY + rs.idx), rs.lap ^ 1u, "attn_tc3 mma S empty");
-        tcgen05_fence_after();
-        const uint32_t kb0 = sKV + r.idx * C::SLOT_BYTES;
+        for (int s2 = 0; s2 < nb; ++s2) {
+          mbar_wait(bar(B_KVFULL + r.idx), r.lap, "attn_tc3 mma K");
+          tcgen05_fence_after();
+          const uint32_t kb0 = sKV + r.idx * C::SLOT_BYTES;
 #pragma unroll
-        for (int g = 0; g < C::G; ++g)
+          for (int g = 0; g < C::G; ++g)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tS + BK * rs.idx, make_desc_sw128(sQ + g * 16384, 16, 1024) + 2u * k,
-                      make_desc_sw128(kb0 + g * (BK * 128), 16, 1024) + 2u * k, idesc_qk, (g | k) != 0 ? 1u : 0u);
-        umma_commit(bar(B_KVEMPTY + r.idx));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tS + C::KT * rs.idx + BK * s2, make_desc_sw128(sQcur + g * 16384, 16, 1024) + 2u * k,
+                        make_desc_sw128(kb0 + g * (BK * 128), 16, 1024) + 2u * k, idesc_qk, (g | k) != 0 ? 1u : 0u);
+          umma_commit(bar(B_KVEMPTY + r.idx));
+          r.next(C::NSLOT);
+        }
         umma_commit(bar(B_SFULL + rs.idx));
-        r.next(C::NSLOT);
         rs.next(2);
       };
       int it = 0;
@@ -165,53 +178,77 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         int seq, h, qt;
         decode(item, seq, h, qt);
         const int n = blocks_of(qt);
-        auto pv = [&](int j) {  // O (+)= P[rp.idx] V_blk
+        auto pv = [&](int tl, int nb) {  // O (+)= P[rp.idx] V_tile
           mbar_wait(bar(B_PFULL + rp.idx), rp.lap, "attn_tc3 mma P");
-          mbar_wait(bar(B_KVFULL + r.idx), r.lap, "attn_tc3 mma V");
-          if (j == 0 && it > 0) mbar_wait(bar(B_OEMPTY), (it - 1) & 1, "attn_tc3 mma O empty");  // previous epilogue drained O
-          tcgen05_fence_after();
-          const uint32_t vb = sKV + r.idx * C::SLOT_BYTES, pb = sP + rp.idx * C::P_BYTES;
+          if (tl == 0 && it > 0) mbar_wait(bar(B_OEMPTY), (it - 1) & 1, "attn_tc3 mma O empty");  // previous epilogue drained O
+          for (int s2 = 0; s2 < nb; ++s2) {
+            mbar_wait(bar(B_KVFULL + r.idx), r.lap, "attn_tc3 mma V");
+            tcgen05_fence_after();
+            const uint32_t vb = sKV + r.idx * C::SLOT_BYTES, pb = sP + rp.idx * C::P_BYTES + s2 * 16384;
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks)
-            umma_bf16(tO, make_desc_sw128(pb, 16, 1024) + 2u * ks, make_desc_sw128(vb + ks * 2048, BK * 128, 1024), idesc_pv,
-                      (j | ks) != 0 ? 1u : 0u);
-          umma_commit(bar(B_KVEMPTY + r.idx));
+            for (int ks = 0; ks < BK / 16; ++ks)
+              umma_bf16(tO, make_desc_sw128(pb, 16, 1024) + 2u * ks, make_desc_sw128(vb + ks * 2048, BK * 128, 1024), idesc_pv,
+                        (tl | s2 | ks) != 0 ? 1u : 0u);
+            umma_commit(bar(B_KVEMPTY + r.idx));
+            r.next(C::NSLOT);
+          }
           umma_commit(bar(B_PEMPTY + rp.idx));
-          r.next(C::NSLOT);
           rp.next(2);
         };
-        mbar_wait(bar(B_QFULL), it & 1, "attn_tc3 mma Q");
-        for (int b = 0; b < n; ++b) qk();  // pass 1
-        for (int b = 0; b < n; ++b) {      // pass 2
-          qk();
-          if (b > 0) pv(b - 1);
+        const int nt = (n + C::ST - 1) / C::ST;
+        auto nb_of = [&](int tl) { return min(C::ST, n - C::ST * tl); };
+        const int qb = C::QBUF == 2 ? (it & 1) : 0;
+        sQcur = sQ + qb * C::Q_BYTES;
+        mbar_wait(bar(B_QFULL + qb), C::QBUF == 2 ? ((it >> 1) & 1) : (it & 1), "attn_tc3 mma Q");
+        for (int tl = 0; tl < nt; ++tl) qk(nb_of(tl));  // pass 1
+        for (int tl = 0; tl < nt; ++tl) {               // pass 2
+          qk(nb_of(tl));
+          if (tl == nt - 1) umma_commit(bar(B_QEMPTY + qb));  // every Q K^T of this item has read the query buffer
+          if (tl > 0) pv(tl - 1, C::ST);
         }
-        pv(n - 1);
+        pv(nt - 1, nb_of(nt - 1));
         umma_commit(bar(B_OFULL));
       }
     }
   } else if (warp == 18) {
     if (lane == 0) {
-      // ===== query loads + output stores (the staging tile is the query buffer) =====
+      // ===== query loads + output stores =====
+      auto load_q = [&](int item, int qb) {
+        int seq, h, qt;
+        decode(item, seq, h, qt);
+        mbar_expect_tx(bar(B_QFULL + qb), C::Q_BYTES);
+#pragma unroll
+        for (int g = 0; g < C::G; ++g) tma_load_3d(sQ + qb * C::Q_BYTES + g * 16384, &tm_q, bar(B_QFULL + qb), h * DH + 64 * g, 128 * qt, seq);
+      };
       int it = 0;
+      if (C::QBUF == 2 && static_cast<int>(blockIdx.x) < n_items) load_q(blockIdx.x, 0);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         int seq, h, qt;
         decode(item, seq, h, qt);
-        mbar_expect_tx(bar(B_QFULL), C::Q_BYTES);
-#pragma unroll
-        for (int g = 0; g < C::G; ++g) tma_load_3d(sQ + g * 16384, &tm_q, bar(B_QFULL), h * DH + 64 * g, 128 * qt, seq);
         const int next = item + gridDim.x;
-        if (next < n_items) {  // the next query tile into L2
-          int s2, h2, q2;
-          decode(next, s2, h2, q2);
+        if (C::QBUF == 2) {
+          // the next item's query tile into the other buffer as soon as the item before this one has released it
+          if (next < n_items) {
+            const int nb = (it + 1) & 1;
+            if (it >= 1) mbar_wait(bar(B_QEMPTY + nb), ((it - 1) >> 1) & 1, "attn_tc3 Q empty");
+            load_q(next, nb);
+          }
+        } else {
+          load_q(item, 0);  // (single buffer: free since the previous item's output store has read it)
+          if (next < n_items) {  // the next query tile into L2
+            int s2, h2, q2;
+            decode(next, s2, h2, q2);
 #pragma unroll
-          for (int g = 0; g < C::G; ++g) tma_prefetch_l2_3d(&tm_q, h2 * DH + 64 * g, 128 * q2, s2);
+            for (int g = 0; g < C::G; ++g) tma_prefetch_l2_3d(&tm_q, h2 * DH + 64 * g, 128 * q2, s2);
+          }
         }
         mbar_wait(bar(B_OUTFULL), it & 1, "attn_tc3 store");
+        const uint32_t stg = C::QBUF == 2 ? sP : sQ;
 #pragma unroll
-        for (int g = 0; g < C::G; ++g) tma_store_3d(&tm_o, sQ + g * 16384, h * DH + 64 * g, 128 * qt, seq);
+        for (int g = 0; g < C::G; ++g) tma_store_3d(&tm_o, stg + g * 16384, h * DH + 64 * g, 128 * qt, seq);
         bulk_commit();
-        bulk_wait_read_all();  // the staging tile has been read: the next query tile may land
+        bulk_wait_read_all();  // the staging tile has been read
+        if (C::QBUF == 2) mbar_arrive(bar(B_STGFREE));  // ... the P buffers may take the next item's probabilities
       }
       bulk_wait_all();
     }
@@ -241,11 +278,14 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       // keys of block b this thread owns: j = 64 b + 16 part + e; a block is `full` when every key is valid for every row
       const int full_blocks = CAUSAL ? min(128 * qt + 1, T) / BK : T / BK;
-      uint32_t s[16];
-      auto next_scores = [&]() {
+      const int nt = (n + C::ST - 1) / C::ST;
+      uint32_t s[C::ST][16];
+      auto next_scores = [&](int nb) {  // this thread's 16 keys of each of the tile's nb blocks, all loads in flight before one wait
         mbar_wait(bar(B_SFULL + rs.idx), rs.lap, "attn_tc3 softmax S");
         tcgen05_fence_after();
-        tmem_ld16(tS + lane_off + BK * rs.idx + 16 * part, s);
+#pragma unroll
+        for (int s2 = 0; s2 < C::ST; ++s2)
+          if (s2 < nb) tmem_ld16(tS + lane_off + C::KT * rs.idx + BK * s2 + 16 * part, s[s2]);
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -255,18 +295,25 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---- pass 1: row maximum of the raw scores (the ALiBi bias is <= 0, so max_j s_j * scale bounds the logits) ----
       float mloc = -INFINITY;
 #pragma unroll 1
-      for (int b = 0; b < n; ++b) {
-        next_scores();
-        if (b < full_blocks) {
+      for (int tl = 0; tl < nt; ++tl) {
+        const int nb = min(C::ST, n - C::ST * tl);
+        next_scores(nb);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) mloc = fmaxf(mloc, __uint_as_float(s[e]));
-        } else {
-          const int j0 = BK * b + 16 * part;
+        for (int s2 = 0; s2 < C::ST; ++s2) {
+          const int b = C::ST * tl + s2;
+          if (s2 < nb) {
+            if (b < full_blocks) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int j = j0 + e;
-            const bool ok = j < T && (!CAUSAL || j <= t);
-            mloc = fmaxf(mloc, ok ? __uint_as_float(s[e]) : -INFINITY);
+              for (int e = 0; e < 16; ++e) mloc = fmaxf(mloc, __uint_as_float(s[s2][e]));
+            } else {
+              const int j0 = BK * b + 16 * part;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int j = j0 + e;
+                const bool ok = j < T && (!CAUSAL || j <= t);
+                mloc = fmaxf(mloc, ok ? __uint_as_float(s[s2][e]) : -INFINITY);
+              }
+            }
           }
         }
       }
@@ -278,29 +325,37 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float l = 0.f;
       const float* tb = tab + 128 + t;  // tb[-j] = bias(t - j)
 #pragma unroll 1
-      for (int b = 0; b < n; ++b) {
-        next_scores();
-        const int j0 = BK * b + 16 * part;
-        float p[16];
-        if (CAUSAL) {
-          const float* tk = tb - j0;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) p[e] = fast_exp2(fmaf(__uint_as_float(s[e]), scale2, tk[-e] - m2));
-        } else if (b < full_blocks) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) p[e] = fast_exp2(fmaf(__uint_as_float(s[e]), scale2, -m2));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) p[e] = j0 + e < T ? fast_exp2(fmaf(__uint_as_float(s[e]), scale2, -m2)) : 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) l += p[e];
+      for (int tl = 0; tl < nt; ++tl) {
+        const int nb = min(C::ST, n - C::ST * tl);
+        next_scores(nb);
+        if (C::QBUF == 2 && tl == 0 && it > 0) mbar_wait(bar(B_STGFREE), (it - 1) & 1, "attn_tc3 softmax staging");  // (long since done)
         mbar_wait(bar(B_PEMPTY + rp.idx), rp.lap ^ 1u, "attn_tc3 softmax P empty");
-        const uint32_t prow = sP + rp.idx * C::P_BYTES + r * 128;
-        st_shared_v4(prow + (((2 * part) ^ rsw) << 4), pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
-                     pack_bf16x2(p[6], p[7]));
-        st_shared_v4(prow + (((2 * part + 1) ^ rsw) << 4), pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
-                     pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
+#pragma unroll
+        for (int s2 = 0; s2 < C::ST; ++s2) {
+          if (s2 < nb) {
+            const int b = C::ST * tl + s2;
+            const int j0 = BK * b + 16 * part;
+            float p[16];
+            if (CAUSAL) {
+              const float* tk = tb - j0;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) p[e] = fast_exp2(fmaf(__uint_as_float(s[s2][e]), scale2, tk[-e] - m2));
+            } else if (b < full_blocks) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) p[e] = fast_exp2(fmaf(__uint_as_float(s[s2][e]), scale2, -m2));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) p[e] = j0 + e < T ? fast_exp2(fmaf(__uint_as_float(s[s2][e]), scale2, -m2)) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) l += p[e];
+            const uint32_t prow = sP + rp.idx * C::P_BYTES + s2 * 16384 + r * 128;
+            st_shared_v4(prow + (((2 * part) ^ rsw) << 4), pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
+                         pack_bf16x2(p[6], p[7]));
+            st_shared_v4(prow + (((2 * part + 1) ^ rsw) << 4), pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]),
+                         pack_bf16x2(p[12], p[13]), pack_bf16x2(p[14], p[15]));
+          }
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_PFULL + rp.idx));
@@ -320,7 +375,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int col = part * (DH / 4) + 16 * c;  // first of 16 output columns
-        const uint32_t grp = sQ + (col >> 6) * 16384 + r * 128;
+        const uint32_t grp = (C::QBUF == 2 ? sP : sQ) + (col >> 6) * 16384 + r * 128;
         const int ch = (col & 63) >> 3;
         uint32_t o[8];
 #pragma unroll

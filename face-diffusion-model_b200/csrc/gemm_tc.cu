@@ -12,10 +12,11 @@
 //   warp 1      MMA issuer     (one elected lane)         tcgen05.mma 128 x BLOCK_N x 16, cta_group::1
 //   warps 2-9   epilogue       (TMEM lane quadrant = warp & 3, column half = (warp-2)/4), double-buffered TMEM accumulator
 // Pipelines: full/empty mbarriers (TMA <-> MMA), tmem_full/tmem_empty mbarriers (MMA <-> epilogue).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 #include <string.h>
+
+using namespace tc;
 
 namespace {
 
@@ -66,152 +67,9 @@ struct Epilogue {
   int32_t stats_parts;
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 26)) {  // watchdog: a protocol bug must trap, never hang the GPU
-      printf("fdm gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0, int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-
-// ---- cta_group::2 (CTA pair) variants -----------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(cta)
-      : "memory");
-}
-// TMA load issued by either CTA of a pair; completes on the LEADER CTA's mbarrier (peer bit masked off)
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0, int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// commit: arrive (once the MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (ignored for swizzled K-major) | [32,46) SBO>>4 = 1024B (8 rows x 128B)
-//   [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
-// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, K-major A and B.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
-  return (1u << 4)                              // c_format = F32
-         | (1u << 7)                            // a_format = BF16
-         | (1u << 10)                           // b_format = BF16
-         | (0u << 15) | (0u << 16)              // a_major, b_major = K
-         | (static_cast<uint32_t>(n >> 3) << 17)
-         | (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05 / TMEM / TMA / mbarrier PTX wrappers: tc_common.cuh (shared by every tensor-core kernel of the library)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) { return make_desc_sw128(smem_addr, 16, 1024); }
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) { return make_idesc_bf16(m, n, 0); }
 
 // ---- epilogue ----------------------------------------------------------------------------------------
 // One thread owns one accumulator row (TMEM lane). A chunk is 128 bytes of output per row (64 bf16 or 32 fp32
@@ -333,9 +191,6 @@ __device__ __forceinline__ void epilogue_math(float (&v)[32], const Epilogue& ep
   }
 }
 
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -343,15 +198,6 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // staging tile: 32 rows x 128 bytes, 16-byte chunk index XOR (row & 7) == CU_TENSOR_MAP_SWIZZLE_128B
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) { return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
 // Tensor maps of the low halves of split-bf16 operands. The plain kernels carry an empty struct: a producer that picks its
@@ -778,27 +624,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_tmapEncodeTiled get_encode_fn() {
-  static PFN_tmapEncodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
-  }
-  return fn;
-}
-
 // 2-D bf16 tensor map: inner extent `cols` (contiguous), `rows` rows with `ld` elements between rows,
 // box = 64 x box_rows, 128-byte swizzle, out-of-bounds reads return zero.
 int make_tmap(CUtensorMap* out, const void* ptr, int64_t cols, int64_t rows, int64_t ld, int box_rows, int box_cols = BLOCK_K,
               bool f32 = false) {
-  PFN_tmapEncodeTiled enc = get_encode_fn();
+  PFN_tmapEncodeTiled enc = tmap_encode_fn();
   FDM_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
@@ -977,13 +807,16 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   // CTA-pair kernel (256 x 256 tiles) whenever there is at least one tile per SM pair and C can go through TMA
   static const bool two_cta = [] { const char* e = getenv("FDM_B200_GEMM_2CTA"); return !(e && e[0] == '0'); }();
   if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2) {
-    // 256 x 128 tiles when the 256 x 256 schedule leaves the last wave mostly empty (N = 1024 at M = 25344: 396 tiles on 74
-    // CTA pairs = 5.35 waves, 89 % of six; 792 half-width tiles fill 97 % of eleven). FDM_B200_GEMM_BN128: 0 never, 1 always.
-    static const int bn128 = [] { const char* e = getenv("FDM_B200_GEMM_BN128"); return e ? atoi(e) : -1; }();
+    // 256 x 128 tiles (FDM_B200_GEMM_BN128=1) for schedules whose last 256 x 256 wave is mostly empty (N = 1024 at M = 25344:
+    // 396 tiles on 74 CTA pairs = 5.35 waves, 89 % of six; 792 half-width tiles fill 97 % of eleven)
+    static const int bn128 = [] { const char* e = getenv("FDM_B200_GEMM_BN128"); return e ? atoi(e) : 0; }();
     const int64_t pairs = sms / 2, t256 = ceil_div64(a.M, 256) * ceil_div64(a.N, 256), t128 = ceil_div64(a.M, 256) * ceil_div64(a.N, 128);
     const double e256 = static_cast<double>(t256) / (pairs * ceil_div64(t256, pairs));
     const double e128 = static_cast<double>(t128) / (pairs * ceil_div64(t128, pairs));
-    if (bn128 == 1 || (bn128 < 0 && e256 < 0.92 && e128 > e256 + 0.05)) return launch<128, 2>(a, ep, s);
+    (void)e256; (void)e128;
+    // measured (profiles/README.md, r02): the half-width tiles lose more in the main loop (each A tile feeds half the MMA
+    // work per shared-memory fetch) than the fuller last wave returns - out-projection 55.4 -> 71.4 us - so this is opt-in
+    if (bn128 == 1) return launch<128, 2>(a, ep, s);
     return launch<256, 2>(a, ep, s);
   }
   if (a.N >= 128 && m_tiles * ceil_div64(a.N, 128) >= sms) return launch<128>(a, ep, s);

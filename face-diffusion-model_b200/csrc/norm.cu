@@ -365,7 +365,7 @@ __device__ __forceinline__ void load8f(const float* p, float (&o)[8]) {
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
-template <int D, int R>
+template <int D, int R, bool RES>
 __global__ void __launch_bounds__(128) layernorm_cols_kernel(const fdm_norm_args a) {
   constexpr int TPR = D / 8;     // threads per row
   constexpr int WPR = TPR / 32;  // warps per row: 4 (d = 1024) or 2 (d = 512)
@@ -382,15 +382,25 @@ __global__ void __launch_bounds__(128) layernorm_cols_kernel(const fdm_norm_args
   load8f(a.b1 + col0, b1);
   pdl_wait();
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(a.x);
-  uint4 xr[R];
+  uint4 xr[R], rr[RES ? R : 1];
 #pragma unroll
   for (int i = 0; i < R; ++i) xr[i] = *reinterpret_cast<const uint4*>(xp + min(row_base + i * RPP, last) * a.ldx + col0);
-  float m[R], q[R];
+  if (RES) {  // residual rows (x + f(x) formed here in fp32: the sum is never rounded to bf16)
+    const __nv_bfloat16* r1p = reinterpret_cast<const __nv_bfloat16*>(a.r1);
+#pragma unroll
+    for (int i = 0; i < R; ++i) rr[i] = *reinterpret_cast<const uint4*>(r1p + min(row_base + i * RPP, last) * a.ldr1 + col0);
+  }
+  float m[R], q[R], v[R][8];
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    float v[8];
-    unpack8(xr[i], v);
-    local_stat<8>(v, m[i], q[i]);
+    unpack8(xr[i], v[i]);
+    if (RES) {
+      float t[8];
+      unpack8(rr[i], t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] += t[e];
+    }
+    local_stat<8>(v[i], m[i], q[i]);
   }
   stat_reduce_scatter<R>(m, q, lane);
   if ((lane & (32 / R - 1)) == 0) st[stat_row<R>(lane)][sub][wr] = make_float2(m[0], q[0]);
@@ -409,17 +419,15 @@ __global__ void __launch_bounds__(128) layernorm_cols_kernel(const fdm_norm_args
 #pragma unroll
     for (int w = 0; w < WPR; ++w) M2 = fmaf((pm[w] - mean) * (pm[w] - mean), 256.f, M2);
     const float rstd = 1.f / sqrtf(M2 * (1.f / D) + a.eps), nmr = -mean * rstd;
-    float v[8];
-    unpack8(xr[i], v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fmaf(fmaf(v[e], rstd, nmr), g1[e], b1[e]);
+    for (int e = 0; e < 8; ++e) v[i][e] = fmaf(fmaf(v[i][e], rstd, nmr), g1[e], b1[e]);
     const int64_t row = row_base + i * RPP;
-    if (row <= last) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + col0) = pack8(v);
+    if (row <= last) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + col0) = pack8(v[i]);
   }
 }
 
 // fused pair: out = LN(LN(x; g1, b1) + r2[row % r2_rows] + vec2[*vec_index_dev]; g2, b2), one warp per row
-template <int D>
+template <int D, bool RES>
 __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args a, const int rows_per_cta) {
   constexpr int NCH = D / 256;  // 16-byte chunks per lane: chunk k covers columns (32 k + lane) * 8 ...
   constexpr int EPL = NCH * 8;
@@ -445,14 +453,28 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
   const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.r2);
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * rows_per_cta + warp; row < row_end; row += 8) {
     const int64_t rr = a.r2_rows > 0 ? (row < a.r2_rows ? row : (row < 2 * a.r2_rows ? row - a.r2_rows : row % a.r2_rows)) : row;
-    uint4 xr[NCH], cr[NCH];
+    uint4 xr[NCH], cr[NCH], r1r[RES ? NCH : 1];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) xr[k] = *reinterpret_cast<const uint4*>(xp + row * a.ldx + (32 * k + lane) * 8);
+    if (RES) {
+      const __nv_bfloat16* r1p = reinterpret_cast<const __nv_bfloat16*>(a.r1) + row * a.ldr1;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) r1r[k] = *reinterpret_cast<const uint4*>(r1p + (32 * k + lane) * 8);
+    }
 #pragma unroll
     for (int k = 0; k < NCH; ++k) cr[k] = *reinterpret_cast<const uint4*>(rp + rr * a.ldr2 + (32 * k + lane) * 8);
     float v[EPL];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) unpack8(xr[k], v + 8 * k);
+    if (RES) {  // x + f(x) formed in fp32 (the sum is never rounded to bf16)
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        float t[8];
+        unpack8(r1r[k], t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[8 * k + e] += t[e];
+      }
+    }
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       float m, q;
@@ -492,7 +514,7 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
   }
 }
 
-template <int D>
+template <int D, bool RES>
 bool launch_hot_ln(const fdm_norm_args& a, bool pair, cudaStream_t s) {
   if (pair) {
     // ~3 CTAs of 8 warps per SM, each staging the 16 KB (d = 1024) of parameters once for its share of the rows
@@ -500,21 +522,22 @@ bool launch_hot_ln(const fdm_norm_args& a, bool pair, cudaStream_t s) {
     int64_t per = ceil_div64(a.rows, ctas);
     per = (per + 7) / 8 * 8;
     const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, per));
-    return fdm_launch_pdl(layernorm_pair_kernel<D>, dim3(grid), dim3(256), 0, s, 1, a, static_cast<int>(per)) == cudaSuccess;
+    return fdm_launch_pdl(layernorm_pair_kernel<D, RES>, dim3(grid), dim3(256), 0, s, 1, a, static_cast<int>(per)) == cudaSuccess;
   }
   constexpr int R = 4;
   const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, R * (128 * 8 / D)));
-  return fdm_launch_pdl(layernorm_cols_kernel<D, R>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
+  return fdm_launch_pdl(layernorm_cols_kernel<D, R, RES>, dim3(grid), dim3(128), 0, s, 1, a) == cudaSuccess;
 }
 // bf16 plain / fused-pair LayerNorm of the denoiser step. FDM_B200_LN_HOT: 0 = warp-per-two-rows kernel for both,
 // 1 = new plain kernel only, 2 = both (default)
 bool try_hot_ln(const fdm_norm_args& a, cudaStream_t s) {
   static const int mode = [] { const char* e = getenv("FDM_B200_LN_HOT"); return e ? atoi(e) : 2; }();
-  if (mode <= 0 || a.x_dtype != FDM_BF16 || a.r1 || a.act1 != FDM_ACT_NONE || !a.g1) return false;
+  if (mode <= 0 || a.x_dtype != FDM_BF16 || a.act1 != FDM_ACT_NONE || !a.g1) return false;
   const bool plain = !a.g2, pair = a.g2 && a.r2 && a.vec2;
   if (!(plain || (pair && mode >= 2))) return false;
-  if (a.d == 1024) return launch_hot_ln<1024>(a, pair, s);
-  if (a.d == 512) return launch_hot_ln<512>(a, pair, s);
+  const bool res = a.r1 != nullptr;  // (same dtype / alignment as x: checked by the caller)
+  if (a.d == 1024) return res ? launch_hot_ln<1024, true>(a, pair, s) : launch_hot_ln<1024, false>(a, pair, s);
+  if (a.d == 512) return res ? launch_hot_ln<512, true>(a, pair, s) : launch_hot_ln<512, false>(a, pair, s);
   return false;
 }
 

@@ -51,6 +51,8 @@ class DenoiserEngine:
         self.lanes = int(os.environ.get("FDM_B200_LANES", "1"))
         self._side = None
         self.fold = False
+        # bf16 mode: residual adds inside the LayerNorm kernels (FDM_B200_RES_IN_LN=0: in the GEMM epilogues, as in fp32 / x3 mode)
+        self.res_in_ln = self.dtype == torch.bfloat16 and os.environ.get("FDM_B200_RES_IN_LN", "1") != "0"
         self._pool = {}          # name -> persistent device buffer (stable addresses keep captured step graphs valid)
         self.graph_cache = {}    # sampler step graphs, keyed by every address / scalar baked into them
 
@@ -272,6 +274,16 @@ class DenoiserEngine:
                 lib.gemm(x, L["qkv_w"], qkv, bias=L["qkv_b"])
                 lib.self_attention(qkv[:, 0:], qkv[:, d:], qkv[:, 2 * d:], att, n * B, T, T, P.heads, P.dh, scale,
                                    slopes=w["slopes"], period=P.period)
+                if self.res_in_ln:
+                    # the residual adds x + f(x) happen inside the LayerNorm kernels, in fp32: the sums are never rounded to
+                    # bf16 (two of the seven bf16 roundings per layer gone) and the GEMMs lose their residual epilogue
+                    lib.gemm(att, L["o_w"], proj, bias=L["o_b"])
+                    lib.layernorm(proj, x, r1=x, g1=L["n1_w"], b1=L["n1_b"], r2=self.cross[l], vec2=L["time_cross"],
+                                  vec_index_dev=t_dev, g2=L["n2_w"], b2=L["n2_b"])
+                    lib.gemm(x, L["f1_w"], ffn, bias=L["f1_b"], act=lib.ACT_RELU)
+                    lib.gemm(ffn, L["f2_w"], proj, bias=L["f2_b"])
+                    lib.layernorm(proj, x, r1=x, g1=L["n3_w"], b1=L["n3_b"])
+                    continue
                 lib.gemm(att, L["o_w"], proj, bias=L["o_b"], residual=x)
                 lib.layernorm(proj, x, g1=L["n1_w"], b1=L["n1_b"], r2=self.cross[l], vec2=L["time_cross"],
                               vec_index_dev=t_dev, g2=L["n2_w"], b2=L["n2_b"])

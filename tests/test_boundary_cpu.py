@@ -154,3 +154,18 @@ def test_bench_reference_arm_contract():
     import bench
     args = bench.parse.__globals__["argparse"].Namespace(preset="vocaset", clips=64, seconds=1.0, ddpm_steps=1000, no_cfg=False)
     assert line["config"] == bench.workload_config(args, 1)  # the two arms of the driver's ratio describe the same workload
+
+
+def test_resample_filter_matches_scipy_design():
+    """Host-side filter design of the device resampler == scipy.signal.resample_poly's own (firwin, Kaiser beta 5)."""
+    import numpy as np
+    from scipy import signal
+    from fdm_b200.frontend import resample_filter
+    for orig in (44100, 48000, 22050, 8000):
+        taps, up, down, pre = resample_filter(orig, 16000)
+        max_rate = max(up, down)
+        half_len = 10 * max_rate
+        h = signal.firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)) * up
+        n_pre_pad = down - half_len % down
+        assert np.abs(taps.numpy() - np.concatenate([np.zeros(n_pre_pad), h])).max() < 1e-14
+        assert pre == (half_len + n_pre_pad) // down

@@ -275,6 +275,19 @@ def test_layernorm_hot_modes(cuda_dev, d, rows, offset):
     ref2 = F.layer_norm(ref + r2.float().repeat(rows // half, 1) + vec[3], (d,), g2, b2)
     assert _rel(out[:rows], ref2) < 4e-3
     assert float(out[rows].float().min()) == 7.0
+    # residual added inside the kernel (x + r1 in fp32), written in place over the residual rows
+    res = mk(rows + 1, d).bfloat16()
+    res[rows] = 7.0
+    refr = F.layer_norm(x.float() + res[:rows].float(), (d,), g1, b1)
+    buf = res.clone()
+    lib.layernorm(x, buf[:rows], r1=buf[:rows], g1=g1, b1=b1)
+    assert _rel(buf[:rows], refr) < 4e-3
+    assert float(buf[rows].float().min()) == 7.0
+    buf = res.clone()
+    lib.layernorm(x, buf[:rows], r1=buf[:rows], g1=g1, b1=b1, r2=r2, vec2=vec, vec_index_dev=idx, g2=g2, b2=b2)
+    refr2 = F.layer_norm(refr + r2.float().repeat(rows // half, 1) + vec[3], (d,), g2, b2)
+    assert _rel(buf[:rows], refr2) < 4e-3
+    assert float(buf[rows].float().min()) == 7.0
 
 
 def _alibi_mask(H, T, period):
@@ -562,3 +575,27 @@ def test_misc_kernels(cuda_dev):
     torch.cuda.synchronize()
     assert _rel(out[:, :Lout], ref) < 1e-5
     assert (out[:, Lout:] == 0).all()
+
+
+@pytest.mark.parametrize("orig_sr", [44100, 48000, 22050, 8000])
+def test_resample_poly_vs_scipy(cuda_dev, orig_sr):
+    """Device polyphase resampler (the demos' librosa.load(sr=16000) step) against
+    scipy.signal.resample_poly on the same float64 filter design; two clips of different content in one launch."""
+    from scipy import signal
+    import numpy as np
+    from fdm_b200 import frontend
+    rs = np.random.RandomState(orig_sr)
+    L = orig_sr // 2 + 37
+    x = rs.randn(2, L).astype(np.float32)
+    x[1] = np.sin(2 * np.pi * 440.0 * np.arange(L) / orig_sr).astype(np.float32)
+    got = frontend.resample(torch.from_numpy(x).to(cuda_dev), orig_sr, 16000)
+    taps, up, down, pre = frontend.resample_filter(orig_sr, 16000)
+    ref = np.stack([signal.resample_poly(x[i].astype(np.float64), up, down) for i in range(2)])
+    assert got.shape == ref.shape
+    assert np.abs(got.cpu().numpy() - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    # the whole front-end: resample + normalise + 1 s of zeros
+    full = frontend.prepare_audio(torch.from_numpy(x).to(cuda_dev), sample_rate=orig_sr)
+    assert full.shape == (2, ref.shape[1] + 16000)
+    want = (ref - ref.mean(1, keepdims=True)) / np.sqrt(ref.var(1, keepdims=True) + 1e-7)
+    assert np.abs(full[:, :ref.shape[1]].cpu().numpy() - want).max() < 1e-4
+    assert float(full[:, ref.shape[1]:].abs().max()) == 0.0
