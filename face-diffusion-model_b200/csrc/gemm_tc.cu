@@ -804,6 +804,13 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   // Tile width: the widest tile that still yields at least one tile per SM; narrow problems fall to 64.
   const int64_t m_tiles = ceil_div64(a.M, BLOCK_M);
   const int sms = fdm_sm_count();
+  {  // experiments: FDM_B200_GEMM_FORCE = 2562 | 1282 | 1281 | 641 forces <BLOCK_N, CG> wherever it is legal
+    static const int force = [] { const char* e = getenv("FDM_B200_GEMM_FORCE"); return e ? atoi(e) : 0; }();
+    if (force == 2562 && ep.tma_c && a.N >= 256 && a.M >= 512) return launch<256, 2>(a, ep, s);
+    if (force == 1282 && ep.tma_c && a.N >= 128 && a.M >= 512) return launch<128, 2>(a, ep, s);
+    if (force == 1281 && a.N >= 128) return launch<128>(a, ep, s);
+    if (force == 641) return launch<64>(a, ep, s);
+  }
   // CTA-pair kernel (256 x 256 tiles) whenever there is at least one tile per SM pair and C can go through TMA
   static const bool two_cta = [] { const char* e = getenv("FDM_B200_GEMM_2CTA"); return !(e && e[0] == '0'); }();
   if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2) {

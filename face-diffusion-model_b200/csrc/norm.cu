@@ -426,25 +426,32 @@ __global__ void __launch_bounds__(128) layernorm_cols_kernel(const fdm_norm_args
   }
 }
 
-// fused pair: out = LN(LN(x; g1, b1) + r2[row % r2_rows] + vec2[*vec_index_dev]; g2, b2), one warp per row
-template <int D, bool RES>
-__global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args a, const int rows_per_cta) {
+// one warp per row. PAIR: out = LN(LN(x [+ r1]; g1, b1) + r2[row % r2_rows] + vec2[*vec_index_dev]; g2, b2); else: out = LN(x [+ r1]; g1, b1)
+template <int D, bool RES, bool PAIR>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const fdm_norm_args a, const int rows_per_cta) {
   constexpr int NCH = D / 256;  // 16-byte chunks per lane: chunk k covers columns (32 k + lane) * 8 ...
   constexpr int EPL = NCH * 8;
-  __shared__ float4 sp[4][D / 4];  // gamma1, beta1 + time row, gamma2, beta2
+  // gamma1, beta1 (+ time row), gamma2, beta2; float4 i of an array (columns 4 i ...) lives at psw(i): the two float4 a lane
+  // needs per chunk are 32 float4 apart, so a quarter-warp's 16-byte reads are conflict-free
+  __shared__ float4 sp[PAIR ? 4 : 2][D / 4];
+  auto psw = [](int i) { return ((i >> 6) * 2 + (i & 1)) * 32 + ((i >> 1) & 31); };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_trigger();
   for (int i = tid; i < D / 4; i += 256) {
-    sp[0][i] = __ldg(reinterpret_cast<const float4*>(a.g1) + i);
-    sp[2][i] = __ldg(reinterpret_cast<const float4*>(a.g2) + i);
-    sp[3][i] = __ldg(reinterpret_cast<const float4*>(a.b2) + i);
+    sp[0][psw(i)] = __ldg(reinterpret_cast<const float4*>(a.g1) + i);
+    if (PAIR) {
+      sp[2][psw(i)] = __ldg(reinterpret_cast<const float4*>(a.g2) + i);
+      sp[3][psw(i)] = __ldg(reinterpret_cast<const float4*>(a.b2) + i);
+    } else {
+      sp[1][psw(i)] = __ldg(reinterpret_cast<const float4*>(a.b1) + i);
+    }
   }
   pdl_wait();
-  {
+  if (PAIR) {
     const float4* vec = reinterpret_cast<const float4*>(a.vec2 + static_cast<int64_t>(*a.vec_index_dev) * D);
     for (int i = tid; i < D / 4; i += 256) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(a.b1) + i), t = __ldg(vec + i);
-      sp[1][i] = make_float4(b.x + t.x, b.y + t.y, b.z + t.z, b.w + t.w);
+      sp[1][psw(i)] = make_float4(b.x + t.x, b.y + t.y, b.z + t.z, b.w + t.w);
     }
   }
   __syncthreads();
@@ -452,8 +459,8 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(a.x);
   const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.r2);
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * rows_per_cta + warp; row < row_end; row += 8) {
-    const int64_t rr = a.r2_rows > 0 ? (row < a.r2_rows ? row : (row < 2 * a.r2_rows ? row - a.r2_rows : row % a.r2_rows)) : row;
-    uint4 xr[NCH], cr[NCH], r1r[RES ? NCH : 1];
+    const int64_t rr = !PAIR ? 0 : (a.r2_rows > 0 ? (row < a.r2_rows ? row : (row < 2 * a.r2_rows ? row - a.r2_rows : row % a.r2_rows)) : row);
+    uint4 xr[NCH], cr[PAIR ? NCH : 1], r1r[RES ? NCH : 1];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) xr[k] = *reinterpret_cast<const uint4*>(xp + row * a.ldx + (32 * k + lane) * 8);
     if (RES) {
@@ -461,8 +468,10 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
 #pragma unroll
       for (int k = 0; k < NCH; ++k) r1r[k] = *reinterpret_cast<const uint4*>(r1p + (32 * k + lane) * 8);
     }
+    if (PAIR) {
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) cr[k] = *reinterpret_cast<const uint4*>(rp + rr * a.ldr2 + (32 * k + lane) * 8);
+      for (int k = 0; k < NCH; ++k) cr[k] = *reinterpret_cast<const uint4*>(rp + rr * a.ldr2 + (32 * k + lane) * 8);
+    }
     float v[EPL];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) unpack8(xr[k], v + 8 * k);
@@ -476,7 +485,7 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
       }
     }
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < (PAIR ? 2 : 1); ++pass) {
       float m, q;
       local_stat<EPL>(v, m, q);
       float n_half = 0.5f * EPL;
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
       for (int k = 0; k < NCH; ++k) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float4 g = sp[2 * pass][(32 * k + lane) * 2 + h], b = sp[2 * pass + 1][(32 * k + lane) * 2 + h];
+          const float4 g = sp[2 * pass][(2 * k + h) * 32 + lane], b = sp[2 * pass + 1][(2 * k + h) * 32 + lane];
           float* o = v + 8 * k + 4 * h;
           o[0] = fmaf(fmaf(o[0], rstd, nmr), g.x, b.x);
           o[1] = fmaf(fmaf(o[1], rstd, nmr), g.y, b.y);
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
           o[3] = fmaf(fmaf(o[3], rstd, nmr), g.w, b.w);
         }
       }
-      if (pass == 0) {
+      if (PAIR && pass == 0) {
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
           float c[8];
@@ -516,13 +525,15 @@ __global__ void __launch_bounds__(256) layernorm_pair_kernel(const fdm_norm_args
 
 template <int D, bool RES>
 bool launch_hot_ln(const fdm_norm_args& a, bool pair, cudaStream_t s) {
-  if (pair) {
-    // ~3 CTAs of 8 warps per SM, each staging the 16 KB (d = 1024) of parameters once for its share of the rows
-    const int64_t ctas = 3 * static_cast<int64_t>(fdm_sm_count());
+  static const int plain_rows = [] { const char* e = getenv("FDM_B200_LN_PLAIN_ROWS"); return e ? atoi(e) : 1; }();
+  if (pair || plain_rows) {
+    // ~3 CTAs of 8 warps per SM, each staging the parameters (16 KB for the pair at d = 1024) once for its share of the rows
+    const int64_t ctas = (pair ? 3 : 4) * static_cast<int64_t>(fdm_sm_count());
     int64_t per = ceil_div64(a.rows, ctas);
     per = (per + 7) / 8 * 8;
     const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, per));
-    return fdm_launch_pdl(layernorm_pair_kernel<D, RES>, dim3(grid), dim3(256), 0, s, 1, a, static_cast<int>(per)) == cudaSuccess;
+    if (pair) return fdm_launch_pdl(layernorm_rows_kernel<D, RES, true>, dim3(grid), dim3(256), 0, s, 1, a, static_cast<int>(per)) == cudaSuccess;
+    return fdm_launch_pdl(layernorm_rows_kernel<D, RES, false>, dim3(grid), dim3(256), 0, s, 1, a, static_cast<int>(per)) == cudaSuccess;
   }
   constexpr int R = 4;
   const unsigned grid = static_cast<unsigned>(ceil_div64(a.rows, R * (128 * 8 / D)));

@@ -18,9 +18,13 @@ for rows, d in ((25344, 1024), (12736, 512)):
     vec = torch.randn(1000, d, device=dev)
     idx = torch.tensor([500], dtype=torch.int32, device=dev)
     out = torch.empty_like(x)
+    res = torch.randn(rows, d, device=dev).bfloat16()
     for name, f, nbytes in (("plain", lambda: lib.layernorm(x, out, g1=g1, b1=b1), 2 * rows * d * 2),
                             ("pair", lambda: lib.layernorm(x, out, g1=g1, b1=b1, r2=r2, vec2=vec, vec_index_dev=idx, g2=g2, b2=b2),
-                             2 * rows * d * 2 + rows // 2 * d * 2)):
+                             2 * rows * d * 2 + rows // 2 * d * 2),
+                            ("plain+res", lambda: lib.layernorm(x, out, r1=res, g1=g1, b1=b1), 3 * rows * d * 2),
+                            ("pair+res", lambda: lib.layernorm(x, out, r1=res, g1=g1, b1=b1, r2=r2, vec2=vec, vec_index_dev=idx, g2=g2, b2=b2),
+                             3 * rows * d * 2 + rows // 2 * d * 2)):
         for _ in range(3):
             f()
         ts = []
