@@ -214,6 +214,59 @@ def test_mead_forward_mask_cond_kwarg(cuda_dev):
     assert torch.equal(fdm.mask_cond(z, force_mask=True), torch.zeros_like(z)) and torch.equal(fdm.mask_cond(z), z)
 
 
+def test_reference_sample_step_body_runs_on_the_drop_in(cuda_dev, tmp_path):
+    """The body of the reference's sample_step (samples/sample_diffusion_mead.py:67-86) - audioencoder(audio) for the length,
+    diffusion.sample(audio, (1, length * 8, 64), emo, id), autoencoder.quant(result, emo), autoencoder.decode(quanted) +
+    template, np.save - executed statement for statement on the drop-in classes with a synthetic one-clip loader (the FLAME
+    template is a given vertex tensor: torch2mesh is reference code off the hot path). In fp32 mode with shared host noise the
+    saved vertices equal the oracle's within 1e-4; the same body then runs in the default bf16 mode with in-kernel noise."""
+    from oracle import reference_ops as R
+    from oracle.weights import host_noise
+    fdm, ae, diff, sd, audio, idh, emo, hiddens, P = _setup("mead", cuda_dev, "fp32")
+    template = torch.randn(1, 1, 15069, generator=torch.Generator().manual_seed(5))
+    loader = [(audio.cpu(), None, template, emo.cpu(), idh.cpu(), ["clip0.wav"])]
+    dev, audioencoder, autoencoder, diffusion, save_folder = cuda_dev, fdm.audio_encoder, ae, diff, str(tmp_path)
+    steps = list(range(999, -1, -50)) + [0]  # (every 50th step keeps the CPU oracle in seconds; the body below is the script's)
+    shape = None
+
+    @torch.no_grad()
+    def sample_step(test_loader, **sample_kw):
+        for n, (audio, _, template, emo_one_hot, id_one_hot, file_name) in enumerate(test_loader):
+            audio = audio.to(dev)
+            template = template.to(dev)
+            emo_one_hot = emo_one_hot.to(dev)
+            id_one_hot = id_one_hot.to(dev)
+            length = audioencoder(audio).last_hidden_state.shape[1] // 2
+            result = diffusion.sample(audio, (1, length * 8, 64), emo_one_hot, id_one_hot, **sample_kw)
+            quanted, _, _ = autoencoder.quant(result, emo_one_hot)
+            output_motion = autoencoder.decode(quanted) + template
+            output_motion = output_motion.detach().cpu().numpy()
+            np.save(os.path.join(save_folder, file_name[0][:-4]), output_motion)
+        return length
+
+    # fp32 mode, host noise shared with the oracle
+    T = hiddens[0].shape[0] // 2
+    shape = (T * 8, 64)
+    diff.noise_source = lambda t: host_noise(99, 0, t, shape)[None]
+    length = sample_step(loader, x_T=host_noise(99, 0, 1000, shape)[None], steps=steps)
+    assert length == T
+    got = np.load(os.path.join(save_folder, "clip0.npy"))
+    assert got.shape == (1, T, 15069) and got.dtype == np.float32
+    tabs = R.diffusion_tables(1000)
+    den = lambda z, t: R.fdm_forward(sd, "mead", hiddens[0], t, z, idh.cpu(), emo.cpu())
+    ref_lat = R.p_sample_loop(tabs, den, host_noise(99, 0, 1000, shape), lambda t: host_noise(99, 0, t, shape), steps=steps)
+    aesd = {k: v.detach().cpu() for k, v in ae.state_dict().items()}
+    ridx, rzq, _ = R.vq_quantize(ref_lat, aesd["quantize.embedding.weight"], emo_pos=int(emo.argmax()))
+    ref = (R.vq_decode(aesd, "mead", rzq) + template[0]).numpy()
+    assert np.abs(got[0] - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+    # default mode (bf16, in-kernel Philox noise, all 1000 steps): the unchanged call of the script
+    fdm.set_precision("bf16"); ae.set_precision("bf16")
+    diff.noise_source = "philox"
+    sample_step(loader)
+    got2 = np.load(os.path.join(save_folder, "clip0.npy"))
+    assert got2.shape == (1, T, 15069) and np.isfinite(got2).all()
+
+
 def test_decode_shortcut_follows_the_tensor_not_its_address(cuda_dev):
     """decode() reused the row buffer of an earlier quant() for ANY tensor at the same address. The rows now
     travel with the tensor object quant() returned; a different tensor at a recycled address must be decoded itself."""
