@@ -173,6 +173,44 @@ __global__ void __launch_bounds__(256) resample_poly_kernel(const float* __restr
   out[static_cast<int64_t>(blockIdx.y) * L_out + m] = acc;
 }
 
+// By-products of VectorQuantizer.forward that the sampling scripts discard but the API returns (models/lib/quantizer.py:52-61):
+// sum over all elements of (z_q - z)^2 (the commitment / codebook loss is (1 + beta) * mean) and the code histogram behind
+// the perplexity. One pass over z and the indices (the winning code rows come from the L2-resident codebook) instead of
+// torch's three passes over (rows, D) temporaries. One warp per row; per-block partial sums in a fixed order (the host adds
+// the `gridDim.x` partials), integer atomics for the histogram: deterministic.
+__global__ void __launch_bounds__(256) vq_stats_kernel(const float* __restrict__ z, const float* __restrict__ codebook,
+                                                       const int64_t* __restrict__ code_offset, const int64_t* __restrict__ indices,
+                                                       int64_t rows, int64_t L, int D, int n_codes, float* __restrict__ partials,
+                                                       unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int sh_hist[];  // n_codes counters, then 8 floats
+  float* red = reinterpret_cast<float*>(sh_hist + n_codes);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n_codes; i += blockDim.x) sh_hist[i] = 0u;
+  __syncthreads();
+  float acc = 0.f;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    const int64_t idx = indices[row];
+    const int64_t off = code_offset ? code_offset[row / L] : 0;
+    const float* zr = z + row * D;
+    const float* er = codebook + (off + idx) * D;
+    for (int k = lane; k < D; k += 32) {
+      const float d = __ldg(er + k) - zr[k];
+      acc = fmaf(d, d, acc);
+    }
+    if (lane == 0 && idx >= 0 && idx < n_codes) atomicAdd(&sh_hist[idx], 1u);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partials[blockIdx.x] = s;
+  }
+  for (int i = threadIdx.x; i < n_codes; i += blockDim.x)
+    if (sh_hist[i]) atomicAdd(hist + i, static_cast<unsigned long long>(sh_hist[i]));
+}
+
 // One CTA per frame: reduce over a vertex subset the squared L2 distance between prediction and ground truth
 // (metric/metric.py:115-138: per-frame max for LVE / FVE / all-vertex error, per-frame mean for EME).
 __global__ void __launch_bounds__(256) vertex_error_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int64_t V,
@@ -291,6 +329,20 @@ extern "C" int fdm_resample_poly(const float* audio, int64_t B, int64_t L_in, fl
   dim3 grid(static_cast<unsigned>(ceil_div64(L_out, 256)), static_cast<unsigned>(B));
   resample_poly_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(audio, L_in, out, L_out, taps, static_cast<int>(n_taps),
                                                                                 static_cast<int>(up), static_cast<int>(down), pre);
+  FDM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fdm_vq_stats(const float* z, const float* codebook, const int64_t* code_offset, const int64_t* indices, int64_t B,
+                            int64_t L, int64_t D, int64_t n_codes, float* sqerr_partials, int64_t n_partials, int64_t* hist,
+                            void* stream) {
+  FDM_CHECK_ARG(z && codebook && indices && sqerr_partials && hist && B > 0 && L > 0 && D > 0 && D <= 1024 && n_codes > 0 &&
+                    n_codes <= 8192 && n_partials > 0 && n_partials <= 65535,
+                "fdm_vq_stats: bad arguments");
+  const size_t smem = static_cast<size_t>(n_codes) * 4 + 32;
+  vq_stats_kernel<<<static_cast<unsigned>(n_partials), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      z, codebook, code_offset, indices, B * L, L, static_cast<int>(D), static_cast<int>(n_codes), sqerr_partials,
+      reinterpret_cast<unsigned long long*>(hist));
   FDM_CHECK_LAUNCH();
   return 0;
 }

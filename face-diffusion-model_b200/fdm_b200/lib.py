@@ -72,6 +72,7 @@ EXPORTS = {
     "fdm_philox_normal": (C.c_int, [_vp, _i64, _i64, _u64, _i64, _i32, _vp]),
     "fdm_vq_quantize": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "fdm_vq_quantize_ex": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "fdm_vq_stats": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "fdm_split_bf16x2": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "fdm_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "fdm_cast_rows": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
@@ -444,6 +445,21 @@ def audio_normalize_pad(audio: torch.Tensor, pad_samples: int = 0, eps: float = 
     _check(require_device().fdm_audio_normalize_pad(_ptr(audio), B, L, _ptr(out), L + pad_samples, eps, _stream()))
     _launched()
     return out
+
+
+def vq_stats(z: torch.Tensor, codebook: torch.Tensor, indices: torch.Tensor, n_codes: int,
+             code_offset: Optional[torch.Tensor] = None):
+    """(sum of (e_idx - z)^2 over all elements as a 0-d fp64 tensor, code histogram int64[n_codes]) in one pass over z."""
+    assert z.dtype == torch.float32 and z.dim() == 3 and z.is_contiguous() and codebook.dtype == torch.float32 and codebook.is_contiguous()
+    assert indices.dtype == torch.int64 and indices.is_contiguous() and indices.numel() == z.shape[0] * z.shape[1]
+    B, L, D = z.shape
+    n_part = int(min(4 * 148, max(1, (B * L + 7) // 8)))
+    partials = torch.empty(n_part, device=z.device, dtype=torch.float32)
+    hist = torch.zeros(n_codes, device=z.device, dtype=torch.int64)
+    _check(require_device().fdm_vq_stats(_ptr(z), _ptr(codebook), _ptr(code_offset), _ptr(indices), B, L, D, n_codes,
+                                         _ptr(partials), n_part, _ptr(hist), _stream()))
+    _launched()
+    return partials.double().sum(), hist
 
 
 def resample_poly(audio: torch.Tensor, taps: torch.Tensor, up: int, down: int, pre: int, n_out: int) -> torch.Tensor:

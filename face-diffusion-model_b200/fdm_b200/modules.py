@@ -616,17 +616,18 @@ class VQAutoEncoderBase(nn.Module):
         if self.emotion_sliced and one_hot is None:
             raise TypeError("quant() of the emotion EVQ-VAE needs the emotion one-hot")
         z = x.detach().float().contiguous()
+        n_codes = self.n_local if self.emotion_sliced else self.args.n_embed
         with lib.nvtx_range("quantize"):
-            idx, zq, zr = quantize(z, self.quantize.embedding.weight, self.n_local if self.emotion_sliced else self.args.n_embed,
-                                   one_hot if self.emotion_sliced else None, want_bdl=True, want_rows=True)
+            idx, zq, zr, sq, hist = quantize(z, self.quantize.embedding.weight, n_codes, one_hot if self.emotion_sliced else None,
+                                             want_bdl=True, want_rows=True, want_stats=True)
         # decode() shortcut: the row layout the quantiser kernel already produced travels WITH the returned tensor
         # (an attribute of that tensor object, valid for its current version), never keyed on an address
         zq._fdm_rows = (zr, zq._version)
-        # loss / perplexity are by-products the sampling scripts discard; computed from the kernel outputs
-        mse = torch.mean((zr - z) ** 2)
+        # loss / perplexity are by-products the sampling scripts discard; one fused pass over z (fdm_vq_stats) instead of
+        # torch's (rows, D) temporaries: loss = beta * mse + mse (models/lib/quantizer.py:52-53), perplexity from the histogram
+        mse = (sq / z.numel()).float()
         loss = self.quantize.beta * mse + mse
-        n_codes = self.n_local if self.emotion_sliced else self.args.n_embed
-        e_mean = torch.bincount(idx.view(-1), minlength=n_codes).float() / idx.numel()
+        e_mean = hist.float() / idx.numel()
         perplexity = torch.exp(-torch.sum(e_mean * torch.log(e_mean + 1e-10)))
         one_hot_enc = None
         if self.return_one_hot:

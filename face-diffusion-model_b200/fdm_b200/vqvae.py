@@ -218,9 +218,10 @@ class VQDecoderEngine:
 
 
 def quantize(z: torch.Tensor, codebook: torch.Tensor, n_local: int, emo_one_hot: Optional[torch.Tensor] = None,
-             want_bdl: bool = True, want_rows: bool = False):
+             want_bdl: bool = True, want_rows: bool = False, want_stats: bool = False):
     """z (B, L, D) fp32. Per-clip emotion slice: offset = n_local * argmax(one_hot[b]) (the reference takes a
-    global argmax because it only ever sees B = 1, models/vq_vae_emotion.py:223)."""
+    global argmax because it only ever sees B = 1, models/vq_vae_emotion.py:223). want_stats: also the by-products of the
+    reference forward (sum of squared quantisation errors as a 0-d fp64 tensor, code histogram) from one more pass over z."""
     z = z.contiguous().float()
     B = z.shape[0]
     off = None
@@ -232,5 +233,9 @@ def quantize(z: torch.Tensor, codebook: torch.Tensor, n_local: int, emo_one_hot:
         if pos.numel() == 1 and B > 1:
             pos = pos.expand(B)
         off = (pos * n_local).contiguous()
-    return lib.vq_quantize(z, codebook.detach().float().contiguous(), n_local, code_offset=off, want_bdl=want_bdl,
-                           want_rows=want_rows)
+    cb = codebook.detach().float().contiguous()
+    idx, zq, zr = lib.vq_quantize(z, cb, n_local, code_offset=off, want_bdl=want_bdl, want_rows=want_rows)
+    if want_stats:
+        sq, hist = lib.vq_stats(z, cb, idx.view(-1), n_local, code_offset=off)
+        return idx, zq, zr, sq, hist
+    return idx, zq, zr

@@ -224,6 +224,13 @@ int fdm_vq_quantize_ex(const float* z, const float* codebook, const int64_t* cod
                        int64_t B, int64_t L, int64_t D, int64_t n_codes,
                        int64_t* indices, float* zq_bdl, float* zq_rows, int32_t algo,
                        uint64_t* recheck_rows, float* dbg_acc, void* stream);
+/* By-products of VectorQuantizer.forward (models/lib/quantizer.py:52-61, models/vq_vae_emotion.py:240-250) from the chosen
+ * indices in one pass over z: sqerr_partials[n_partials] = per-block partial sums of (e_idx - z)^2 over all elements (the
+ * caller adds them; loss = (1 + beta) * sum / (rows * D)), hist[n_codes] += code usage counts (caller zero-fills; perplexity
+ * = exp(-sum p log(p + 1e-10))). code_offset as in fdm_vq_quantize (per-clip slice; indices are slice-local). */
+int fdm_vq_stats(const float* z, const float* codebook, const int64_t* code_offset, const int64_t* indices, int64_t B,
+                 int64_t L, int64_t D, int64_t n_codes, float* sqerr_partials, int64_t n_partials, int64_t* hist,
+                 void* stream);
 
 /* ---- small data-movement kernels ------------------------------------------------------------ */
 /* hi = bf16(x), lo = bf16(x - hi): the operand pair of the split-bf16 GEMM (fdm_gemm_args.A_lo / W_lo). n elements. */

@@ -87,6 +87,13 @@ def test_chain_quant_decode_fp32(cuda_dev, preset, graph):
     oidx, ozq, margin = R.vq_quantize(z[0].cpu(), ae.quantize.embedding.weight.detach().cpu(), emo_pos)
     assert torch.equal(idx[:, 0].cpu(), oidx)
     assert torch.equal(zq[0].cpu(), ozq)
+    # by-products (models/lib/quantizer.py:52-61): loss = beta * mse + mse, perplexity from the code usage
+    zf = z[0].cpu().double()
+    mse_ref = ((ozq.t().double() - zf) ** 2).mean()
+    assert abs(float(loss) - 1.25 * float(mse_ref)) <= 1e-5 * float(mse_ref) * 1.25 + 1e-12
+    e_mean = torch.bincount(oidx, minlength=256).double() / oidx.numel()
+    ppl_ref = torch.exp(-(e_mean * torch.log(e_mean + 1e-10)).sum())
+    assert abs(float(ppl) - float(ppl_ref)) <= 1e-4 * float(ppl_ref)
     robust = g["vq_margin_reference"] > 1e-5
     assert np.array_equal(idx[:, 0].cpu().numpy()[robust], g["vq_idx_reference"][robust])
     verts = ae.decode(zq)
