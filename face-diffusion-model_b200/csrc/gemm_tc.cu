@@ -56,6 +56,7 @@ struct Epilogue {
   int32_t res_dtype, out_dtype, act;
   int32_t tma_c, vec_r, vec_bias;  // C through TMA stores; 16-byte vector access legal for residual / bias
   int32_t tma_r;                   // bf16 residual tiles fetched by TMA into the staging tile (needs tma_c, bf16 out)
+  int32_t lin_c;                   // fp32 C whose row pitch is not a multiple of 16 bytes (N = 15069, 70110: the vertex maps)
   int32_t M;
   // LayerNorm folding (see fdm_gemm_args): consumer correction, residual rebuilt from un-normalised rows, output statistics
   const float* a_ln;
@@ -580,9 +581,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             bulk_commit();
           }
         } else {
-          // C rows are not 16-byte aligned (e.g. N = 15069 fp32): coalesced element stores, one row per iteration
+          // C rows are not 16-byte aligned (N = 15069 / 70110 fp32: the vertex maps; TMA needs 16-byte aligned box starts, which
+          // no tensor map over such a pitch can give): coalesced element stores, one row per iteration. fp32 fast path: the
+          // warp stores a full 32-column row per instruction, eight rows' shared-memory reads in flight at a time.
           __syncwarp();
           const int esz = out_bf16 ? 2 : 4;
+          if (!out_bf16 && col0 + 32 <= N) {
+            const int nr = min(32, M - row_w);
+            float* cp = reinterpret_cast<float*>(ep.C) + static_cast<int64_t>(row_w) * ep.ldc + col0 + lane;
+            const uint32_t sw = static_cast<uint32_t>(lane >> 2), lo = static_cast<uint32_t>(lane & 3) * 4u;
+#pragma unroll
+            for (int r8 = 0; r8 < 32; r8 += 8) {
+              float fv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = r8 + i;
+                asm("ld.shared.f32 %0, [%1];" : "=f"(fv[i]) : "r"(sbuf + static_cast<uint32_t>(rr) * 128u + ((sw ^ (rr & 7)) << 4) + lo));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (r8 + i < nr) cp[static_cast<int64_t>(r8 + i) * ep.ldc] = fv[i];
+            }
+          } else
           for (int rr = 0; rr < 32; ++rr) {
             const int64_t orow = static_cast<int64_t>(row_w) + rr;
             if (orow >= M) break;
@@ -785,6 +805,8 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   ep.M = static_cast<int32_t>(a.M);
   ep.vec_r = a.residual && aligned16(a.residual) && (a.ldr * rsz) % 16 == 0;
   ep.vec_bias = a.bias && aligned16(a.bias);
+  // fp32 output whose row pitch is not a multiple of 16 bytes (the vertex maps): element stores, but still the big tiles
+  ep.lin_c = !ep.tma_c && a.out_dtype == FDM_F32;
   ep.tma_r = ep.tma_c && a.residual && a.res_dtype == FDM_BF16 && a.out_dtype == FDM_BF16 && aligned16(a.residual) &&
              (a.ldr * 2) % 16 == 0;
   ep.a_ln = a.a_ln;
@@ -813,7 +835,7 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   }
   // CTA-pair kernel (256 x 256 tiles) whenever there is at least one tile per SM pair and C can go through TMA
   static const bool two_cta = [] { const char* e = getenv("FDM_B200_GEMM_2CTA"); return !(e && e[0] == '0'); }();
-  if (two_cta && ep.tma_c && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2) {
+  if (two_cta && (ep.tma_c || ep.lin_c) && a.N >= 256 && a.M >= 512 && ceil_div64(a.M, 256) * ceil_div64(a.N, 256) >= sms / 2) {
     // 256 x 128 tiles (FDM_B200_GEMM_BN128=1) for schedules whose last 256 x 256 wave is mostly empty (N = 1024 at M = 25344:
     // 396 tiles on 74 CTA pairs = 5.35 waves, 89 % of six; 792 half-width tiles fill 97 % of eleven)
     static const int bn128 = [] { const char* e = getenv("FDM_B200_GEMM_BN128"); return e ? atoi(e) : 0; }();

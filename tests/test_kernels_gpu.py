@@ -16,6 +16,7 @@ GEMM_SHAPES = [
     (128, 256, 64), (256, 256, 128), (200, 1024, 1024), (198, 3072, 1024), (792, 1024, 2048),
     (1000, 512, 512), (130, 64, 64), (257, 192, 320), (12672, 1024, 1024), (333, 15069, 1024),
     (5000, 2048, 512), (4099, 1280, 192), (25344, 3072, 1024),  # CTA-pair (cta_group::2) kernel, with M / N / K tails
+    (2100, 15069, 256), (700, 1001, 128),  # fp32 rows that are not 16-byte aligned: 1-D TMA row stores, ragged last chunk
 ]
 
 
