@@ -205,30 +205,41 @@ __global__ void __launch_bounds__(256) vq_stats_kernel(const float* __restrict__
   for (int i = threadIdx.x; i < n_codes; i += blockDim.x) sh_hist[i] = 0u;
   __syncthreads();
   float acc = 0.f;
-  // four rows per warp and iteration (their index loads, then their row loads, in flight together); D = 64: float2 per lane
-  for (int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * 4; row0 < rows; row0 += static_cast<int64_t>(gridDim.x) * 32) {
-    int64_t idx[4];
+  // eight rows per warp and iteration: the index loads and the (index-independent) latent loads go out first, then the code
+  // rows they select (L2-resident); D = 64: float2 per lane
+  constexpr int RW = 8;
+  for (int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * RW; row0 < rows; row0 += static_cast<int64_t>(gridDim.x) * 8 * RW) {
+    if (D == 64) {
+      int64_t idx[RW];
+      float2 a[RW];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) idx[q] = row0 + q < rows ? indices[row0 + q] : -1;
+      for (int q = 0; q < RW; ++q) {
+        const bool ok = row0 + q < rows;
+        idx[q] = ok ? indices[row0 + q] : -1;
+        a[q] = ok ? reinterpret_cast<const float2*>(z + (row0 + q) * 64)[lane] : make_float2(0.f, 0.f);
+      }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (idx[q] < 0) continue;
-      const int64_t row = row0 + q;
-      const int64_t off = code_offset ? code_offset[row / L] : 0;
-      const float* zr = z + row * D;
-      const float* er = codebook + (off + idx[q]) * D;
-      if (D == 64) {
-        const float2 a = reinterpret_cast<const float2*>(zr)[lane], e = __ldg(reinterpret_cast<const float2*>(er) + lane);
-        const float d0 = e.x - a.x, d1 = e.y - a.y;
+      for (int q = 0; q < RW; ++q) {
+        if (idx[q] < 0) continue;
+        const int64_t off = code_offset ? code_offset[(row0 + q) / L] : 0;
+        const float2 e = __ldg(reinterpret_cast<const float2*>(codebook + (off + idx[q]) * 64) + lane);
+        const float d0 = e.x - a[q].x, d1 = e.y - a[q].y;
         acc = fmaf(d0, d0, acc);
         acc = fmaf(d1, d1, acc);
-      } else {
+        if (lane == 0 && idx[q] < n_codes) atomicAdd(&sh_hist[idx[q]], 1u);
+      }
+    } else {
+      for (int q = 0; q < RW && row0 + q < rows; ++q) {
+        const int64_t row = row0 + q, id = indices[row];
+        const int64_t off = code_offset ? code_offset[row / L] : 0;
+        const float* zr = z + row * D;
+        const float* er = codebook + (off + id) * D;
         for (int k = lane; k < D; k += 32) {
           const float d = __ldg(er + k) - zr[k];
           acc = fmaf(d, d, acc);
         }
+        if (lane == 0 && id >= 0 && id < n_codes) atomicAdd(&sh_hist[id], 1u);
       }
-      if (lane == 0 && idx[q] < n_codes) atomicAdd(&sh_hist[idx[q]], 1u);
     }
   }
   acc = warp_sum(acc);

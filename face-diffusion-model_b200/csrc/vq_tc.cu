@@ -778,13 +778,16 @@ __device__ __noinline__ void role_epilogue(const Params& p, const Ctx& cx) {
           }
         }
       }
-      if (out_rows) {  // (B, L, D): the warp copies one 256-byte code row per iteration
+      if (out_rows) {  // (B, L, D): the warp copies two 256-byte code rows per iteration (16 lanes x float4 each)
         const int wrows = min(32, nrows - quad * 32);
-        for (int rr = 0; rr < wrows; ++rr) {
-          if ((deferred >> rr) & 1u) continue;
-          const int ci = __shfl_sync(0xffffffffu, idx, rr);
-          const float2 v = __ldg(reinterpret_cast<const float2*>(cbg + ci * D) + lane);
-          reinterpret_cast<float2*>(out_rows + (b * L + l0 + quad * 32 + rr) * D)[lane] = v;
+        const int sub = lane >> 4, l16 = lane & 15;
+        for (int rr = 0; rr < wrows; rr += 2) {
+          const int r2 = rr + sub;
+          const int ci = __shfl_sync(0xffffffffu, idx, r2 & 31);
+          if (r2 < wrows && !((deferred >> r2) & 1u)) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(cbg + ci * D) + l16);
+            reinterpret_cast<float4*>(out_rows + (b * L + l0 + quad * 32 + r2) * D)[l16] = v;
+          }
         }
       }
       if (quad == 0) TRACE(11);

@@ -453,7 +453,7 @@ def vq_stats(z: torch.Tensor, codebook: torch.Tensor, indices: torch.Tensor, n_c
     assert z.dtype == torch.float32 and z.dim() == 3 and z.is_contiguous() and codebook.dtype == torch.float32 and codebook.is_contiguous()
     assert indices.dtype == torch.int64 and indices.is_contiguous() and indices.numel() == z.shape[0] * z.shape[1]
     B, L, D = z.shape
-    n_part = int(min(4 * 148, max(1, (B * L + 7) // 8)))
+    n_part = int(min(8 * 148, max(1, (B * L + 63) // 64)))
     partials = torch.empty(n_part, device=z.device, dtype=torch.float32)
     hist = torch.zeros(n_codes, device=z.device, dtype=torch.int64)
     _check(require_device().fdm_vq_stats(_ptr(z), _ptr(codebook), _ptr(code_offset), _ptr(indices), B, L, D, n_codes,
