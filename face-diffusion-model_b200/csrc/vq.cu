@@ -156,10 +156,10 @@ int launch_vq(const float* z, const float* codebook, const int64_t* code_offset,
 
 }  // namespace
 
-// tensor-core filter + exact recheck (vq_tc.cu), D = 64
-int fdm_vq_tc_launch(const float* z, const float* codebook, const int64_t* code_offset, int64_t B, int64_t L, int n_codes,
-                     int64_t* indices, float* zq_bdl, float* zq_rows, unsigned long long* recheck_rows, float* dbg_acc,
-                     cudaStream_t stream);
+// tensor-core filter + exact recheck (vq_tc.cu), D = 64 / 128
+int fdm_vq_tc_launch(const float* z, const float* codebook, const int64_t* code_offset, int64_t B, int64_t L, int64_t D,
+                     int n_codes, int64_t* indices, float* zq_bdl, float* zq_rows, unsigned long long* recheck_rows,
+                     float* dbg_acc, cudaStream_t stream);
 
 extern "C" int fdm_vq_quantize_ex(const float* z, const float* codebook, const int64_t* code_offset, int64_t B, int64_t L,
                                   int64_t D, int64_t n_codes, int64_t* indices, float* zq_bdl, float* zq_rows, int32_t algo,
@@ -170,10 +170,10 @@ extern "C" int fdm_vq_quantize_ex(const float* z, const float* codebook, const i
                 "fdm_vq_quantize: z and codebook must be 16-byte aligned");
   FDM_CHECK_ARG(algo >= FDM_VQ_AUTO && algo <= FDM_VQ_TENSOR, "fdm_vq_quantize: unknown algo %d", algo);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (algo == FDM_VQ_AUTO) algo = D == 64 ? FDM_VQ_TENSOR : FDM_VQ_FFMA;
+  if (algo == FDM_VQ_AUTO) algo = (D == 64 || D == 128) ? FDM_VQ_TENSOR : FDM_VQ_FFMA;
   if (algo == FDM_VQ_TENSOR) {
-    FDM_CHECK_ARG(D == 64, "fdm_vq_quantize: the tensor-core path needs D = 64 (got %lld)", (long long)D);
-    return fdm_vq_tc_launch(z, codebook, code_offset, B, L, static_cast<int>(n_codes), indices, zq_bdl, zq_rows,
+    FDM_CHECK_ARG(D == 64 || D == 128, "fdm_vq_quantize: the tensor-core path needs D = 64 or 128 (got %lld)", (long long)D);
+    return fdm_vq_tc_launch(z, codebook, code_offset, B, L, D, static_cast<int>(n_codes), indices, zq_bdl, zq_rows,
                             reinterpret_cast<unsigned long long*>(recheck_rows), dbg_acc, s);
   }
   FDM_CHECK_ARG(!dbg_acc, "fdm_vq_quantize: dbg_acc is a tensor-core path output");

@@ -406,7 +406,7 @@ def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, n_codes: int, code_offs
                 want_rows=False, algo: int = VQ_AUTO, recheck_rows: Optional[torch.Tensor] = None,
                 dbg_acc: Optional[torch.Tensor] = None):
     """z (B, L, D) f32 -> (indices (B*L, 1) int64, z_q (B, D, L) or None, z_q rows (B, L, D) or None).
-    algo: VQ_AUTO (tensor-core filter + exact recheck when D = 64), VQ_FFMA, VQ_TENSOR; identical indices either way.
+    algo: VQ_AUTO (tensor-core filter + exact recheck when D = 64 / 128), VQ_FFMA, VQ_TENSOR; identical indices either way.
     recheck_rows: optional zeroed int64[1] device counter of rows that took the exact pass (tensor path);
     dbg_acc: optional (B*L, n_codes) f32 dump of the tensor-core dot products (tests)."""
     lib = require_device()

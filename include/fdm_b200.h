@@ -213,9 +213,9 @@ int fdm_vq_quantize(const float* z, const float* codebook, const int64_t* code_o
                     int64_t B, int64_t L, int64_t D, int64_t n_codes,
                     int64_t* indices, float* zq_bdl, float* zq_rows, void* stream);
 /* Same contract with an explicit algorithm. FDM_VQ_FFMA evaluates every chain on the fp32 pipes (any D in {32,64,128}).
- * FDM_VQ_TENSOR (D = 64) ranks the codes with a bf16x3 tcgen05 distance GEMM, proves all but a window of near-minimal
+ * FDM_VQ_TENSOR (D = 64 or 128) ranks the codes with a bf16x3 tcgen05 distance GEMM, proves all but a window of near-minimal
  * codes cannot win, and evaluates the exact chains for the survivors only: identical indices, HBM-bound instead of
- * FFMA-bound. FDM_VQ_AUTO picks FDM_VQ_TENSOR when D = 64. recheck_rows (optional, device, caller-zeroed) counts the rows
+ * FFMA-bound. FDM_VQ_AUTO picks FDM_VQ_TENSOR when D = 64 / 128. recheck_rows (optional, device, caller-zeroed) counts the rows
  * that needed the exact pass; dbg_acc (optional, device, [B*L, n_codes] f32) receives the tensor-core dot products. */
 #define FDM_VQ_AUTO 0
 #define FDM_VQ_FFMA 1
