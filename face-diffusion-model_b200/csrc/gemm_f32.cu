@@ -120,6 +120,7 @@ extern "C" int fdm_gemm_f32(const fdm_gemm_args* args, void* stream) {
   FDM_CHECK_ARG(a.M < (1ll << 31) && a.N < (1ll << 31) && a.K < (1ll << 31), "fdm_gemm_f32: dimension too large");
   if (a.taps > 1) FDM_CHECK_ARG(a.tap_k > 0 && a.K == a.taps * a.tap_k, "fdm_gemm_f32: implicit conv needs K == taps*tap_k");
   FDM_CHECK_ARG(!a.a_ln && !a.res_ln && !a.stats_out, "fdm_gemm_f32: LayerNorm folding is a bf16-path feature");
+  FDM_CHECK_ARG(a.a_group_cols == 0, "fdm_gemm_f32: the grouped mode is a bf16-path feature");
   F32Params p;
   p.A = static_cast<const float*>(a.A);
   p.W = static_cast<const float*>(a.W);

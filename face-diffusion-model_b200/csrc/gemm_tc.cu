@@ -108,6 +108,24 @@ __device__ __forceinline__ float act_gelu_erf_fast(float x) {
   const float erf_abs = 1.f - p * t * __expf(-z * z);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
+// erf-GELU for outputs that are rounded to bf16 (plain bf16 GEMMs only: fp32 / split-bf16 outputs keep the 1.5e-7 form above):
+// no MUFU at all. erf(x / sqrt 2) = w P(w^2) with w = clamp(x / (2 R sqrt 2), -1/2, 1/2), R = 2.85, P of degree 7 fitted on
+// Chebyshev nodes with P(1/4) / 2 = 1 pinned, so beyond |x| = 4.03 the result is exactly x or 0. |GELU error| < 1.3e-4
+// (at |x| ~ 4, where a bf16 ulp is 1.6e-2); 13 FMA-pipe instructions per element against ~22 + 2 MUFU: HuBERT's FFN1
+// GEMMs (N = 4096, K = 1024) had their epilogue, not the MMAs, on the critical path (584 vs 813 TFLOP/s for the QKV GEMM).
+__device__ __forceinline__ float act_gelu_erf_poly(float x) {
+  const float w = __saturatef(fmaf(x, 0.12405407f, 0.5f)) - 0.5f;  // 1 / (2 * 2.85 * sqrt 2)
+  const float s = w * w;
+  float p = fmaf(-108514.76f, s, 133392.03f);
+  p = fmaf(p, s, -71527.083f);
+  p = fmaf(p, s, 22276.801f);
+  p = fmaf(p, s, -4549.4910f);
+  p = fmaf(p, s, 653.65449f);
+  p = fmaf(p, s, -69.234234f);
+  p = fmaf(p, s, 6.4296663f);
+  return x * fmaf(0.5f, w * p, 0.5f);
+}
+constexpr int ACT_GELU_ERF_BF16 = 100;  // internal: FDM_ACT_GELU_ERF of a plain bf16-output GEMM
 __device__ __forceinline__ void act_inplace(float (&v)[32], int act) {
   if (act == FDM_ACT_NONE) return;
   if (act == FDM_ACT_RELU) {
@@ -119,6 +137,9 @@ __device__ __forceinline__ void act_inplace(float (&v)[32], int act) {
   } else if (act == FDM_ACT_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = act_gelu_erf_fast(v[j]);
+  } else if (act == ACT_GELU_ERF_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_gelu_erf_poly(v[j]);
   } else if (act == FDM_ACT_GELU_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = act_gelu_tanh_fast(v[j]);
@@ -225,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
                const __grid_constant__ LoMaps<SPLIT> lo, const __grid_constant__ ResMaps<RESMMA> rm, const Epilogue ep,
                const int M, const int N, const int num_k_blocks, const int kb_per_tap, const int tap_row_shift, const int m_tiles,
-               const int n_tiles, const int kb_per_seg) {
+               const int n_tiles, const int kb_per_seg, const int a_group_cols) {
   // num_k_blocks = segments x kb_per_seg. One segment: the plain bf16 GEMM. Three segments (SPLIT, split-bf16 operands): the
   // same K range three times into the same accumulator - A_lo W_hi, A_hi W_lo, A_hi W_hi (small terms first) - only the
   // producer's choice of tensor map differs, the MMA issuer and the epilogue see one long K loop.
@@ -290,6 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         const int a_row = m_blk * (BLOCK_M * CG) + row_in_tile;
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
+        const int a_col0 = n_blk * a_group_cols;  // grouped convolution: output tile n_blk reads its own channel group of A
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const CUtensorMap* ma = &tmap_a;
@@ -306,12 +328,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           if (CG == 1) {
             mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-            tma_load_2d(sa, ma, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
+            tma_load_2d(sa, ma, full_bar(stage), a_col0 + kc * BLOCK_K, a_row + tap * tap_row_shift);
             tma_load_2d(sa + C::A_BYTES, mb, full_bar(stage), ks * BLOCK_K, b_row);
           } else {
             // both CTAs' bytes complete on the leader's barrier; the leader posts the whole transaction count
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-            tma_load_2d_2sm(sa, ma, full_bar(stage), kc * BLOCK_K, a_row + tap * tap_row_shift);
+            tma_load_2d_2sm(sa, ma, full_bar(stage), a_col0 + kc * BLOCK_K, a_row + tap * tap_row_shift);
             tma_load_2d_2sm(sa + C::A_BYTES, mb, full_bar(stage), ks * BLOCK_K, b_row);
             if (cta_rank != 0) mbar_arrive_remote(full_bar(stage), 0);
           }
@@ -692,7 +714,8 @@ int launch_impl(const fdm_gemm_args& a, const Epilogue& ep_in, cudaStream_t stre
     ep.vec_r = 0;
   }
   const int taps = a.taps > 1 ? a.taps : 1;
-  const int64_t a_cols = taps > 1 ? a.tap_k : a.K;
+  // grouped mode: the A map spans every group's columns, the producer moves the window with the N tile
+  const int64_t a_cols = (taps > 1 ? a.tap_k : a.K) * (a.a_group_cols > 0 ? ceil_div64(a.N, BLOCK_N) : 1);
   CUtensorMap tm_a, tm_b, tm_c;
   if (int rc = make_tmap(&tm_a, a.A, a_cols, a.a_rows, a.lda, BLOCK_M)) return rc;
   if (int rc = make_tmap(&tm_b, a.W, a.K, a.N, a.ldw, BLOCK_N / CG)) return rc;
@@ -722,7 +745,8 @@ int launch_impl(const fdm_gemm_args& a, const Epilogue& ep_in, cudaStream_t stre
   const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
   FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
                                 tm_c, tm_r, lo, rm, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks,
-                                kb_per_tap, taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles, kb_per_seg));
+                                kb_per_tap, taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles, kb_per_seg,
+                                static_cast<int>(a.a_group_cols)));
   return 0;
 }
 
@@ -802,6 +826,8 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   ep.res_dtype = a.res_dtype;
   ep.out_dtype = a.out_dtype;
   ep.act = a.act;
+  static const bool gelu_poly = [] { const char* e = getenv("FDM_B200_GELU_POLY"); return !(e && e[0] == '0'); }();
+  if (gelu_poly && a.act == FDM_ACT_GELU_ERF && a.out_dtype == FDM_BF16 && !a.A_lo) ep.act = ACT_GELU_ERF_BF16;
   const int64_t csz = a.out_dtype == FDM_BF16 ? 2 : 4, rsz = a.res_dtype == FDM_BF16 ? 2 : 4;
   ep.tma_c = aligned16(a.C) && (a.ldc * csz) % 16 == 0;
   ep.M = static_cast<int32_t>(a.M);
@@ -828,6 +854,13 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   // Tile width: the widest tile that still yields at least one tile per SM; narrow problems fall to 64.
   const int64_t m_tiles = ceil_div64(a.M, BLOCK_M);
   const int sms = fdm_sm_count();
+  if (a.a_group_cols != 0) {  // grouped convolution: one 64-column tile per group
+    FDM_CHECK_ARG(a.a_group_cols > 0 && a.a_group_cols % BLOCK_K == 0 && a.N % 64 == 0 &&
+                      a.a_group_cols == (a.taps > 1 ? a.tap_k : a.K) && a.lda >= a.a_group_cols * (a.N / 64),
+                  "fdm_gemm_bf16: grouped mode needs N %% 64 == 0, a_group_cols == tap_k (or K) %% 64 == 0 and lda covering every group");
+    FDM_CHECK_ARG(!a.a_ln && !a.res_ln && !a.stats_out, "fdm_gemm_bf16: grouped mode has no LayerNorm folding");
+    return launch<64>(a, ep, s);
+  }
   {  // experiments: FDM_B200_GEMM_FORCE = 2562 | 1282 | 1281 | 641 forces <BLOCK_N, CG> wherever it is legal
     static const int force = [] { const char* e = getenv("FDM_B200_GEMM_FORCE"); return e ? atoi(e) : 0; }();
     if (force == 2562 && ep.tma_c && a.N >= 256 && a.M >= 512) return launch<256, 2>(a, ep, s);

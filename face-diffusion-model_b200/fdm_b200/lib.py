@@ -26,7 +26,8 @@ class GemmArgs(C.Structure):
                 ("residual", _vp), ("ldr", _i64), ("res_dtype", _i32), ("out_dtype", _i32), ("C", _vp),
                 ("ldc", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("act", _i32), ("taps", _i32),
                 ("tap_k", _i64), ("tap_row_shift", _i64), ("a_ln", _vp), ("w_colsum", _vp), ("res_ln", _vp),
-                ("res_gamma", _vp), ("res_beta", _vp), ("stats_out", _vp), ("A_lo", _vp), ("W_lo", _vp)]
+                ("res_gamma", _vp), ("res_beta", _vp), ("stats_out", _vp), ("A_lo", _vp), ("W_lo", _vp),
+                ("a_group_cols", _i64)]
 
 
 class NormArgs(C.Structure):
@@ -226,8 +227,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
          tap_row_shift: int = 0, K: Optional[int] = None, a_ln: Optional[torch.Tensor] = None,
          w_colsum: Optional[torch.Tensor] = None, res_ln: Optional[torch.Tensor] = None,
          res_gamma: Optional[torch.Tensor] = None, res_beta: Optional[torch.Tensor] = None,
-         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         stats_out: Optional[torch.Tensor] = None, a_group_cols: int = 0) -> torch.Tensor:
     """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual; bf16 operands -> tcgen05, f32 -> FFMA.
+    a_group_cols > 0: grouped (block-diagonal) mode of fdm_gemm_bf16, see fdm_gemm_args.a_group_cols.
 
     `a` may be any tensor whose storage holds the rows (lda/a_rows/M override the 2-D view for implicit
     convolutions); `out`/`residual` are 2-D with unit inner stride."""
@@ -262,6 +264,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     g.a_ln, g.w_colsum, g.res_ln = _ptr(a_ln), _ptr(w_colsum), _ptr(res_ln)
     g.res_gamma, g.res_beta, g.stats_out = _ptr(res_gamma), _ptr(res_beta), _ptr(stats_out)
     g.A_lo, g.W_lo = _ptr(a_lo), _ptr(w_lo)
+    g.a_group_cols = a_group_cols
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.numel() >= g.M * (N // 64) * 2
     assert out.shape[0] >= g.M and out.shape[1] == N

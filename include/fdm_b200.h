@@ -88,6 +88,12 @@ typedef struct fdm_gemm_args {
    * a_rows / taps, same ldw). Used by the high-precision steps of the sampler and the once-per-clip audio encoder. */
   const void* A_lo;
   const void* W_lo;
+  /* ---- grouped (block-diagonal) mode, fdm_gemm_bf16 only; 0 = off ------------------------------------------------------
+   * A grouped Conv1d (HF HubertPositionalConvEmbedding: 16 groups of 64 channels, k = 128) as ONE launch: output columns
+   * [64 g, 64 g + 64) are computed from the columns [g * a_group_cols, (g + 1) * a_group_cols) of A (per tap) and rows
+   * [64 g, 64 g + 64) of W, whose K index runs over that group's taps x channels only. Needs N % 64 == 0 and
+   * a_group_cols == tap_k (taps > 1) or == K, a multiple of 64. */
+  int64_t a_group_cols;
 } fdm_gemm_args;
 
 /* Kernel-selection switches of fdm_gemm_bf16 (process-wide; results are identical up to fp32 summation order):

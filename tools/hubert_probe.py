@@ -13,11 +13,16 @@ BATCH = int(os.environ.get("BATCH", "64"))
 SECONDS = float(os.environ.get("SECONDS", "10"))
 fdm, ae, diff = bench.build_models(os.environ.get("PRESET", "vocaset"), dev, "bf16")
 a = bench.synthetic_audio(BATCH, int(16000 * SECONDS), 0).to(dev)
-fdm.encode_audio(a.clone())
+REPS = int(os.environ.get("REPS", "1"))
+if os.environ.get("AUDIO_PRECISION"):
+    fdm.audio_precision = os.environ["AUDIO_PRECISION"]
+for _ in range(2 if REPS > 1 else 1):
+    fdm.encode_audio(a.clone())
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-h = fdm.encode_audio(a.clone())
+for _ in range(REPS):
+    h = fdm.encode_audio(a.clone())
 e1.record()
 torch.cuda.synchronize()
-print("encode ms", e0.elapsed_time(e1), tuple(h.shape))
+print("encode ms", e0.elapsed_time(e1) / REPS, tuple(h.shape))
