@@ -152,6 +152,75 @@ def test_gemm_implicit_conv(cuda_dev, dtype):
     assert _rel(got2, ref2) < (2e-5 if dtype == torch.float32 else 1e-4)
 
 
+@pytest.mark.parametrize("split", [False, True])
+def test_gemm_grouped_conv_one_launch(cuda_dev, split):
+    """HubertPositionalConvEmbedding-shaped grouped Conv1d (groups of 64 channels, zero padding k/2, + GELU + residual) as ONE
+    grouped launch (fdm_gemm_args.a_group_cols) against torch's grouped conv1d; plain bf16 and split-bf16 operands."""
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    B, T, G, cg, k = 3, 70, 5, 64, 16
+    Cn = G * cg
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(B, T, Cn, generator=g).to(cuda_dev)
+    wt = (torch.randn(Cn, cg, k, generator=g) / math.sqrt(k * cg)).to(cuda_dev)
+    bias = torch.randn(Cn, generator=g).to(cuda_dev)
+    if not split:
+        x, wt = x.bfloat16().float(), wt.bfloat16().float()
+    pad = k // 2
+    conv = F.conv1d(x.double().transpose(1, 2), wt.double(), bias.double(), padding=pad, groups=G)[:, :, :T].transpose(1, 2)
+    ref = (F.gelu(conv) + x.double()).float()
+    Tp = (T + 2 * pad + 7) // 8 * 8
+    dt = torch.float32 if split else torch.bfloat16
+    xpad = torch.zeros(B * Tp, Cn, device=cuda_dev, dtype=dt)
+    lib.pad_time(x.to(dt).contiguous(), xpad, B, T, Cn, pad, Tp - T - pad, 0)
+    wk = wt.permute(0, 2, 1).reshape(Cn, k * cg).contiguous().to(dt)  # [Cout, tap, cin of the group]
+    out = torch.zeros(B * Tp, Cn, device=cuda_dev, dtype=dt)
+    Mp = B * Tp - (k - 1)
+    a_op, w_op = (lib.split(xpad), lib.split(wk)) if split else (xpad, wk)
+    lib.gemm(a_op, w_op, out, bias=bias, act=lib.ACT_GELU_ERF, residual=xpad[pad:], M=Mp, lda=Cn, a_rows=B * Tp, taps=k, tap_k=cg,
+             tap_row_shift=1, a_group_cols=cg)
+    torch.cuda.synchronize()
+    got = out.view(B, Tp, Cn)[:, :T].float()
+    assert _rel(got, ref) < (3e-5 if split else 4e-3), _rel(got, ref)   # bf16 output rounding: 2^-9 per element
+    # and it equals the per-group launches it replaces (same kernel, same k order)
+    out_g = torch.zeros_like(out)
+    for gi in range(G):
+        a_g = lib.Split(a_op.hi[:, gi * cg:], a_op.lo[:, gi * cg:]) if split else xpad[:, gi * cg:]
+        w_g = lib.Split(w_op.hi[gi * cg:(gi + 1) * cg], w_op.lo[gi * cg:(gi + 1) * cg]) if split else wk[gi * cg:(gi + 1) * cg]
+        lib.gemm(a_g, w_g, out_g[:, gi * cg:(gi + 1) * cg], bias=bias[gi * cg:(gi + 1) * cg].contiguous(), act=lib.ACT_GELU_ERF,
+                 residual=xpad[pad:, gi * cg:(gi + 1) * cg], M=Mp, lda=Cn, a_rows=B * Tp, taps=k, tap_k=cg, tap_row_shift=1)
+    torch.cuda.synchronize()
+    assert torch.equal(out_g[:Mp], out[:Mp])
+
+
+def test_gemm_gelu_erf_polynomial_epilogue(cuda_dev):
+    """The MUFU-free erf-GELU of plain bf16-output GEMMs (act_gelu_erf_poly): |error| < 1.3e-4 absolute against the exact
+    GELU over the whole input range, i.e. invisible after the bf16 rounding of the output; fp32 outputs keep the 1.5e-7 form."""
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    M, N, K = 256, 128, 64
+    xs = torch.linspace(-12, 12, M * N).view(M, N)
+    a = torch.zeros(M, K, device=cuda_dev, dtype=torch.bfloat16)
+    w = torch.zeros(N, K, device=cuda_dev, dtype=torch.bfloat16)
+    # W = two stacked 64 x 64 identities: out[:, j] = act(A[:, j mod 64]), the accumulator holds the bf16 inputs exactly
+    w[:64] = torch.eye(64, device=cuda_dev, dtype=torch.bfloat16)
+    w[64:] = torch.eye(64, device=cuda_dev, dtype=torch.bfloat16)
+    xa = xs[:, :64].to(cuda_dev).bfloat16()
+    a.copy_(xa)
+    ref = F.gelu(xa.double())
+    ref = torch.cat([ref, ref], 1)
+    out_bf = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    out_f = torch.empty(M, N, device=cuda_dev)
+    lib.gemm(a, w, out_bf, act=lib.ACT_GELU_ERF)
+    lib.gemm(a, w, out_f, act=lib.ACT_GELU_ERF)
+    torch.cuda.synchronize()
+    assert (out_f.double() - ref).abs().max().item() < 2e-6
+    err = (out_bf.double() - ref).abs()
+    assert (err <= 1.3e-4 + ref.abs() * 2.0 ** -8).all(), err.max().item()
+    big = torch.cat([xa.double().abs() > 4.1] * 2, 1)  # beyond the clamp: x (1 + O(1e-6)) or x O(1e-6)
+    assert (err[big] <= 2e-5 * ref[big].abs().clamp_min(1.0) * 12 + ref[big].abs() * 2.0 ** -8).all()
+
+
 @pytest.mark.parametrize("M,d,big", [(600, 1024, False), (333, 512, False), (25344, 1024, True)])
 def test_gemm_layernorm_folding(cuda_dev, M, d, big):
     """LayerNorm folded into the neighbouring GEMMs (fdm_gemm_args a_ln / res_ln / stats_out + fdm_ln_stats_finalize):
