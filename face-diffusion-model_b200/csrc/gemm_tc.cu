@@ -239,12 +239,28 @@ template <> struct LoMaps<true> { CUtensorMap a, b; };
 // per 256 x 256 tile against 8k cycles of MMA (profiles/r01_j_gemm_tc_full.md: tensor pipe 60 % on the out-projection).
 template <bool RESMMA> struct ResMaps {};
 template <> struct ResMaps<true> { CUtensorMap res, ident; };
+// TAILK: split-K for the tiles of a partially filled last wave. A static schedule of `tiles` full tiles on `slots` CTAs (or
+// CTA pairs) leaves slots - rem of them idle during the last wave when rem = tiles mod slots is small (N = 1024 at
+// M = 25344: 396 tiles = 5 waves + 26 on 74 pairs; BIWI at 16 clips per GPU: 76 tiles = 1 wave + 2). With TAILK the last
+// rem tiles are cut along K into S = min(slots / rem, 8, k-blocks / 2) slices, one per CTA (pair), all running in the
+// last wave. A slice writes its fp32 partial accumulator into its own slab of a caller-provided workspace (plain TMA
+// stores: no zero-initialised state, no atomics on data) and bumps a counter per (tile, CTA, epilogue warp) region; the
+// warp that arrives LAST at a region sums the S slabs in slice order (deterministic), applies the epilogue and stores C.
+// No CTA ever waits for another one. Plain TMA-store epilogue only (no TMA residual, folding, split operands, RESMMA).
+template <bool TAILK> struct TailK {};
+template <> struct TailK<true> {
+  CUtensorMap ws;      // fp32 [rem * S * 128 * CG, BLOCK_N] slabs, box 32 x 32
+  const float* slabs;  // the same memory for the finaliser's loads
+  int* counters;       // [rem][CG][EPI_WARPS], zero between launches
+  int num_full, rem, S, kb_per_slice;
+};
 
-template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA>
+template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA, bool TAILK = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-               const __grid_constant__ LoMaps<SPLIT> lo, const __grid_constant__ ResMaps<RESMMA> rm, const Epilogue ep,
+               const __grid_constant__ LoMaps<SPLIT> lo, const __grid_constant__ ResMaps<RESMMA> rm,
+               const __grid_constant__ TailK<TAILK> tk, const Epilogue ep,
                const int M, const int N, const int num_k_blocks, const int kb_per_tap, const int tap_row_shift, const int m_tiles,
                const int n_tiles, const int kb_per_seg, const int a_group_cols) {
   // num_k_blocks = segments x kb_per_seg. One segment: the plain bf16 GEMM. Three segments (SPLIT, split-bf16 operands): the
@@ -270,6 +286,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int row_in_tile = static_cast<int>(cta_rank) * BLOCK_M;
+  // TAILK: full tiles are [0, full_tiles); CTA (pair) p < rem * S then takes slice p % S of tile full_tiles + p / S
+  int full_tiles = num_tiles, tail_tile = -1, tail_slab = 0, tail_kb0 = 0, tail_kb1 = 0;
+  if constexpr (TAILK) {
+    full_tiles = tk.num_full;
+    if (tile_first < tk.rem * tk.S) {
+      const int t = tile_first / tk.S, sl = tile_first - t * tk.S;
+      tail_tile = tk.num_full + t;
+      tail_slab = tile_first;  // = t * S + sl
+      tail_kb0 = sl * tk.kb_per_slice;
+      tail_kb1 = min(tail_kb0 + tk.kb_per_slice, num_k_blocks);
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -278,6 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ep.tma_r) tma_prefetch_desc(&tmap_r);
     if constexpr (SPLIT) { tma_prefetch_desc(&lo.a); tma_prefetch_desc(&lo.b); }
     if constexpr (RESMMA) { tma_prefetch_desc(&rm.res); tma_prefetch_desc(&rm.ident); }
+    if constexpr (TAILK) tma_prefetch_desc(&tk.ws);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), CG);  // CG = 2: leader's expect_tx arrival + the peer's remote arrival
@@ -307,12 +336,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      int tile_done_tail = 0;
+      for (int tile = tile_first; tile < full_tiles || (TAILK && tile_done_tail == 0 && tail_tile >= 0); tile += tile_step) {
+        int kb_begin = 0, kb_end = num_k_blocks;
+        if (TAILK && tile >= full_tiles) { tile = tail_tile; kb_begin = tail_kb0; kb_end = tail_kb1; tile_done_tail = 1; }
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         const int a_row = m_blk * (BLOCK_M * CG) + row_in_tile;
         const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
         const int a_col0 = n_blk * a_group_cols;  // grouped convolution: output tile n_blk reads its own channel group of A
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const CUtensorMap* ma = &tmap_a;
           const CUtensorMap* mb = &tmap_b;
@@ -368,11 +400,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M * CG, BLOCK_N);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      int tail_done = 0;
+      for (int tile = tile_first; tile < full_tiles || (TAILK && tail_done == 0 && tail_tile >= 0); tile += tile_step) {
+        int kb_begin = 0, kb_end = num_k_blocks;
+        if (TAILK && tile >= full_tiles) { tile = tail_tile; kb_begin = tail_kb0; kb_end = tail_kb1; tail_done = 1; }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = base + stage * C::STAGE_BYTES;
@@ -381,8 +416,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs when CG = 2) once these MMAs retire
           if (CG == 2) umma_commit_2sm(empty_bar(stage));
@@ -543,7 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     } else
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+    for (int tile = tile_first; tile < full_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -653,6 +688,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       else mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    if constexpr (TAILK) {
+      if (tail_tile >= 0 && c_end > c_begin) {
+        // ===== K-slice of a tail tile: fp32 partial -> this slice's workspace slab; the last slice to arrive at this warp's
+        //       region (32 rows x this warp's columns) sums the slabs in slice order, applies the epilogue and stores C =====
+        const int m_blk = tail_tile / n_tiles, n_blk = tail_tile - m_blk * n_tiles;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+        const int slab_row = row_in_tile + quad * 32;  // this warp's first row inside a (128 * CG)-row slab
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32, ++g) {
+          if (n_blk * BLOCK_N + c0 >= N) break;  // warp-uniform (nobody reads those columns)
+          const uint32_t sbuf = stage_base + (g % NB_STAGE) * 4096u;
+          if (lane == 0) bulk_wait_read<NB_STAGE - 1>();
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tacc + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_shared_v4(sbuf + stage_off(lane, j), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tk.ws, sbuf, c0, tail_slab * (BLOCK_M * CG) + slab_row);
+            bulk_commit();
+          }
+        }
+        tcgen05_fence_before();
+        if (CG == 2) mbar_arrive_remote(tempty_bar(acc), 0);
+        else mbar_arrive(tempty_bar(acc));
+        const int t_idx = tail_tile - tk.num_full;
+        int* counter = tk.counters + (t_idx * CG + static_cast<int>(cta_rank)) * EPI_WARPS + ew;
+        int arrived = 0;
+        if (lane == 0) {
+          bulk_wait_all();   // this warp's slab stores have COMPLETED (written, not merely read from shared memory)
+          fence_async_all();  // async-proxy writes -> ordered before the generic-proxy release below
+          __threadfence();
+          arrived = atomicAdd(counter, 1);
+        }
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (arrived == tk.S - 1) {
+          __threadfence();  // acquire: every slice's slab rows of this region are visible (read through L2 below)
+          const int row_w = m_blk * (BLOCK_M * CG) + slab_row;
+          const int64_t row = static_cast<int64_t>(row_w) + lane;
+          const bool row_ok = row < M;
+          const uint32_t buf_t = stage_base, buf_o = stage_base + 4096u;  // fp32 transpose scratch, output tile
+          const float* slab0 = tk.slabs + (static_cast<int64_t>(t_idx) * tk.S * (BLOCK_M * CG) + slab_row) * BLOCK_N;
+          const int64_t slab_stride = static_cast<int64_t>(BLOCK_M * CG) * BLOCK_N;
+#pragma unroll 1
+          for (int c0 = c_begin; c0 < c_end; c0 += CW) {
+            const int col0 = n_blk * BLOCK_N + c0;
+            if (col0 >= N) break;  // warp-uniform
+#pragma unroll 1
+            for (int half = 0; half < CW / 32; ++half) {
+              if (col0 + half * 32 >= N) break;  // warp-uniform
+              // coalesced sum of the S slabs: lane -> (row 4 i + lane / 8, columns 4 (lane % 8) .. + 3)
+              float4 acc4[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float* src = slab0 + static_cast<int64_t>(lane >> 3) * BLOCK_N + c0 + half * 32 + 4 * (lane & 7);
+#pragma unroll 1
+              for (int sl = 0; sl < tk.S; ++sl) {
+                float4 x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __ldcg(reinterpret_cast<const float4*>(src + sl * slab_stride + static_cast<int64_t>(4 * i) * BLOCK_N));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { acc4[i].x += x[i].x; acc4[i].y += x[i].y; acc4[i].z += x[i].z; acc4[i].w += x[i].w; }
+              }
+              __syncwarp();  // every lane has finished reading its row of the scratch tile (previous half)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                st_shared_v4(buf_t + stage_off(4 * i + (lane >> 3), lane & 7), __float_as_uint(acc4[i].x), __float_as_uint(acc4[i].y),
+                             __float_as_uint(acc4[i].z), __float_as_uint(acc4[i].w));
+              __syncwarp();
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t q0, q1, q2, q3;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(buf_t + stage_off(lane, j)));
+                v[4 * j] = __uint_as_float(q0); v[4 * j + 1] = __uint_as_float(q1);
+                v[4 * j + 2] = __uint_as_float(q2); v[4 * j + 3] = __uint_as_float(q3);
+              }
+              epilogue_math<false>(v, ep, row, row_ok, col0 + half * 32, N);
+              if (half == 0) {  // the previous chunk's TMA store has finished reading the output tile
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+              }
+              if (out_bf16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  st_shared_v4(buf_o + stage_off(lane, half * 4 + j), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+                               pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  st_shared_v4(buf_o + stage_off(lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+              }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, buf_o, col0, row_w);  // rows >= M and columns >= N are clipped by the tensor map
+              bulk_commit();
+            }
+          }
+          if (lane == 0) atomicExch(counter, 0);  // all S slices have arrived: ready for the next launch
+        }
+      }
+    }
     if (lane == 0) bulk_wait_all();  // all TMA stores of this warp have completed before the CTA retires
   }
 
@@ -692,12 +837,29 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 void* g_identity[64] = {nullptr};
 int g_resmma = -1;  // -1: read FDM_B200_GEMM_RESMMA on first use; fdm_gemm_set_option overrides
 
-template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA>
+// Tail split-K schedule (see TailK): returns S >= 2 when the last wave of `tiles` on `slots` is at most half full
+struct TailPlan { int num_full, rem, S, kb_per_slice; };
+inline bool plan_tail(int64_t tiles, int64_t slots, int num_k_blocks, TailPlan* p) {
+  const int64_t full = tiles / slots * slots, rem = tiles - full;
+  if (rem == 0 || rem * 2 > slots) return false;
+  int S = static_cast<int>(slots / rem);
+  if (S > 8) S = 8;
+  if (S > num_k_blocks / 2) S = num_k_blocks / 2;
+  if (S < 2) return false;
+  const int kbs = (num_k_blocks + S - 1) / S;
+  S = (num_k_blocks + kbs - 1) / kbs;  // no empty slice
+  if (S < 2) return false;
+  p->num_full = static_cast<int>(full); p->rem = static_cast<int>(rem); p->S = S; p->kb_per_slice = kbs;
+  return true;
+}
+constexpr int64_t TAILK_COUNTER_BYTES = 4096;  // counters at the start of the workspace, slabs behind them
+
+template <int BLOCK_N, int CG, bool FOLD, bool SPLIT, bool RESMMA, bool TAILK = false>
 int launch_impl(const fdm_gemm_args& a, const Epilogue& ep_in, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA, TAILK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   Epilogue ep = ep_in;
@@ -742,9 +904,22 @@ int launch_impl(const fdm_gemm_args& a, const Epilogue& ep_in, cudaStream_t stre
   const int64_t tiles = static_cast<int64_t>(m_tiles) * n_tiles;
   static const int sm_limit = [] { const char* e = getenv("FDM_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();  // experiments only
   const int64_t slots = (sm_limit > 0 ? sm_limit : fdm_sm_count()) / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) the device holds
-  const int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
-  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
-                                tm_c, tm_r, lo, rm, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks,
+  int grid = static_cast<int>((tiles < slots ? tiles : slots) * CG);
+  TailK<TAILK> tk;
+  if constexpr (TAILK) {
+    TailPlan tp;
+    const bool ok = plan_tail(tiles, slots, num_k_blocks, &tp);
+    const int64_t need = TAILK_COUNTER_BYTES + static_cast<int64_t>(tp.rem) * tp.S * (BLOCK_M * CG) * BLOCK_N * 4;
+    FDM_CHECK_ARG(ok && a.splitk_ws && a.splitk_ws_bytes >= need && tp.rem * CG * EPI_WARPS * 4 <= TAILK_COUNTER_BYTES,
+                  "fdm_gemm_bf16: internal: tail split-K launched without a plan / workspace");
+    tk.counters = reinterpret_cast<int*>(a.splitk_ws);
+    tk.slabs = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.splitk_ws) + TAILK_COUNTER_BYTES);
+    tk.num_full = tp.num_full; tk.rem = tp.rem; tk.S = tp.S; tk.kb_per_slice = tp.kb_per_slice;
+    if (int rc = make_tmap(&tk.ws, tk.slabs, BLOCK_N, static_cast<int64_t>(tp.rem) * tp.S * (BLOCK_M * CG), BLOCK_N, 32, 32, true)) return rc;
+    if (tp.num_full == 0) grid = tp.rem * tp.S * CG;  // fewer tiles than CTAs: only the slices run
+  }
+  FDM_CHECK_CUDA(fdm_launch_pdl(gemm_tc_kernel<BLOCK_N, CG, FOLD, SPLIT, RESMMA, TAILK>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, CG, tm_a, tm_b,
+                                tm_c, tm_r, lo, rm, tk, ep, static_cast<int>(a.M), static_cast<int>(a.N), num_k_blocks,
                                 kb_per_tap, taps > 1 ? static_cast<int>(a.tap_row_shift) : 0, m_tiles, n_tiles, kb_per_seg,
                                 static_cast<int>(a.a_group_cols)));
   return 0;
@@ -765,6 +940,20 @@ int launch(const fdm_gemm_args& a, const Epilogue& ep, cudaStream_t stream) {
   }
   if (g_resmma == 1 && a.residual && a.res_dtype == FDM_BF16 && a.act == FDM_ACT_NONE && aligned16(a.residual) && (a.ldr * 2) % 16 == 0)
     return launch_impl<BLOCK_N, CG, false, false, true>(a, ep, stream);
+  if constexpr (BLOCK_N == 256 && CG == 2) {
+    // tail split-K (see TailK): plain TMA-store epilogue, workspace given, and a last wave that is at most half full
+    static const bool tailk_on = [] { const char* e = getenv("FDM_B200_GEMM_TAILK"); return !(e && e[0] == '0'); }();
+    if (tailk_on && a.splitk_ws && ep.tma_c && !ep.tma_r && a.a_group_cols == 0) {
+      static const int sm_limit = [] { const char* e = getenv("FDM_B200_GEMM_SMS"); return e ? atoi(e) : 0; }();
+      const int64_t slots = (sm_limit > 0 ? sm_limit : fdm_sm_count()) / CG;
+      const int64_t tiles = ceil_div64(a.M, BLOCK_M * CG) * ceil_div64(a.N, BLOCK_N);
+      TailPlan tp;
+      if (plan_tail(tiles, slots, static_cast<int>(ceil_div64(a.K, BLOCK_K)), &tp) &&
+          a.splitk_ws_bytes >= TAILK_COUNTER_BYTES + static_cast<int64_t>(tp.rem) * tp.S * (BLOCK_M * CG) * BLOCK_N * 4 &&
+          tp.rem * CG * EPI_WARPS * 4 <= TAILK_COUNTER_BYTES)
+        return launch_impl<BLOCK_N, CG, false, false, false, true>(a, ep, stream);
+    }
+  }
   return launch_impl<BLOCK_N, CG, false, false, false>(a, ep, stream);
 }
 
@@ -817,6 +1006,8 @@ extern "C" int fdm_gemm_bf16(const fdm_gemm_args* args, void* stream) {
   FDM_CHECK_ARG(a.out_dtype == FDM_F32 || a.out_dtype == FDM_BF16, "fdm_gemm_bf16: bad out_dtype");
   FDM_CHECK_ARG((a.A_lo == nullptr) == (a.W_lo == nullptr), "fdm_gemm_bf16: split-bf16 operands need both A_lo and W_lo");
   FDM_CHECK_ARG(!a.A_lo || (aligned16(a.A_lo) && aligned16(a.W_lo)), "fdm_gemm_bf16: A_lo and W_lo must be 16-byte aligned");
+  FDM_CHECK_ARG(!a.splitk_ws || ((reinterpret_cast<uintptr_t>(a.splitk_ws) & 255u) == 0 && a.splitk_ws_bytes > 0),
+                "fdm_gemm_bf16: splitk_ws must be 256-byte aligned with splitk_ws_bytes > 0");
   Epilogue ep;
   ep.bias = a.bias;
   ep.residual = a.residual;

@@ -49,6 +49,8 @@ class DenoiserEngine:
         self.T = 0
         self.passes = 1
         self.lanes = int(os.environ.get("FDM_B200_LANES", "1"))
+        if self.lanes == 2:
+            lib.splitk_enabled = False  # two streams run GEMMs concurrently: they must not share the (opt-in) tail split-K workspace
         self._side = None
         self.fold = False
         # bf16 mode: residual adds inside the LayerNorm kernels (FDM_B200_RES_IN_LN=0: in the GEMM epilogues, as in fp32 / x3 mode)

@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
                 ("ldc", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("act", _i32), ("taps", _i32),
                 ("tap_k", _i64), ("tap_row_shift", _i64), ("a_ln", _vp), ("w_colsum", _vp), ("res_ln", _vp),
                 ("res_gamma", _vp), ("res_beta", _vp), ("stats_out", _vp), ("A_lo", _vp), ("W_lo", _vp),
-                ("a_group_cols", _i64)]
+                ("a_group_cols", _i64), ("splitk_ws", _vp), ("splitk_ws_bytes", _i64)]
 
 
 class NormArgs(C.Structure):
@@ -221,6 +221,29 @@ def split(x: torch.Tensor) -> Split:
     return Split(hi, lo)
 
 
+_SPLITK_WS = {}
+SPLITK_WS_BYTES = 20 << 20
+# Off by default: measured slower than the plain schedule in its current form (the finalising warp's dependent global
+# round trips cost 7-14 us per GEMM against 3-6 us saved, profiles/README.md r02_h), and per-element summation order then
+# depends on the tile schedule, i.e. on the batch size. FDM_B200_GEMM_TAILK=1 (or lib.splitk_enabled = True) turns it on.
+splitk_enabled = os.environ.get("FDM_B200_GEMM_TAILK", "0") == "1"
+
+
+def _splitk_workspace(device) -> Optional[torch.Tensor]:
+    """Per-device workspace of the GEMM's tail split-K (fdm_gemm_args.splitk_ws). Kernels ordered on one stream or graph
+    share it; code that runs GEMMs CONCURRENTLY on several streams sets lib.splitk_enabled = False. Never allocated during
+    stream capture (a capture that starts before any eager GEMM on the device simply runs without the split)."""
+    if not splitk_enabled:
+        return None
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _SPLITK_WS.get(idx)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        ws = _SPLITK_WS[idx] = torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
+    return ws
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, *, M: Optional[int] = None,
          lda: Optional[int] = None, a_rows: Optional[int] = None, taps: int = 1, tap_k: int = 0,
@@ -265,6 +288,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, bias: Optional[tor
     g.res_gamma, g.res_beta, g.stats_out = _ptr(res_gamma), _ptr(res_beta), _ptr(stats_out)
     g.A_lo, g.W_lo = _ptr(a_lo), _ptr(w_lo)
     g.a_group_cols = a_group_cols
+    ws = _splitk_workspace(a.device) if (a.dtype == torch.bfloat16 and a_lo is None) else None
+    if ws is not None:
+        g.splitk_ws, g.splitk_ws_bytes = _ptr(ws), ws.numel()
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.numel() >= g.M * (N // 64) * 2
     assert out.shape[0] >= g.M and out.shape[1] == N

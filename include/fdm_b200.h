@@ -94,6 +94,15 @@ typedef struct fdm_gemm_args {
    * [64 g, 64 g + 64) of W, whose K index runs over that group's taps x channels only. Needs N % 64 == 0 and
    * a_group_cols == tap_k (taps > 1) or == K, a multiple of 64. */
   int64_t a_group_cols;
+  /* ---- tail split-K workspace (fdm_gemm_bf16 only; NULL = off) ---------------------------------------------------------
+   * When the static tile schedule leaves the last wave at most half full, the tiles of that wave are cut along K into
+   * slices that run on the otherwise idle SMs; the slices exchange fp32 partial tiles through this DEVICE buffer
+   * (deterministic: fixed summation order). The first 4096 bytes hold counters and must be ZERO before the first use;
+   * the kernel leaves them zero. 256-byte aligned; 20 MB covers every shape (4096 + (SMs / 4) * 8 * 256 KB is the
+   * maximum); a launch whose plan does not fit simply runs without the split. One workspace must not be shared by
+   * launches that may run CONCURRENTLY (different streams); launches ordered on a stream or in a graph can share it. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
 } fdm_gemm_args;
 
 /* Kernel-selection switches of fdm_gemm_bf16 (process-wide; results are identical up to fp32 summation order):

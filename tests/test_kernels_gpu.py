@@ -152,6 +152,55 @@ def test_gemm_implicit_conv(cuda_dev, dtype):
     assert _rel(got2, ref2) < (2e-5 if dtype == torch.float32 else 1e-4)
 
 
+@pytest.mark.parametrize("M,N,K,act,res", [
+    (4768, 1024, 1024, 0, False),    # BIWI at 16 clips per GPU: 76 tiles on 74 CTA pairs -> 2 tail tiles x 8 K-slices
+    (4768, 3072, 1024, 0, False),    # 228 tiles = 3 waves + 6
+    (4768, 1000, 2048, 1, True),     # ragged M and N edges inside the tail tiles, bias + ReLU + fp32 residual in the finaliser
+    (12736, 1536, 512, 3, False),    # MEAD at 32 clips per GPU: 300 tiles = 4 waves + 4, 4 slices of 2 k-blocks
+    (25344, 1024, 2048, 0, False),   # the headline FFN2: 396 tiles = 5 waves + 26 -> 2 slices each
+])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_tail_split_k(cuda_dev, M, N, K, act, res, out_dtype):
+    """Tail split-K (TailK in gemm_tc.cu): the tiles of a sparsely filled last wave are cut along K, partial fp32 tiles meet
+    in the workspace and the last slice to arrive finishes the tile. Checked against torch, against the unsplit kernel,
+    and for run-to-run determinism (fixed summation order: no atomics on data)."""
+    from fdm_b200 import lib
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    r = torch.randn(M, N, generator=g).to(cuda_dev) if res else None
+    fn = {0: lambda x: x, 1: F.relu, 3: F.gelu}[act]
+    ref = fn(a.float() @ w.float().t() + bias) + (r if res else 0)
+    outs = []
+    was = lib.splitk_enabled
+    try:
+        lib.splitk_enabled = True  # opt-in feature (default off)
+        for rep in range(3):
+            out = torch.full((M, N), float("nan"), device=cuda_dev, dtype=out_dtype)
+            lib.gemm(a, w, out, bias=bias, act=act, residual=r)
+            outs.append(out)
+        lib.splitk_enabled = False
+        plain = torch.empty(M, N, device=cuda_dev, dtype=out_dtype)
+        lib.gemm(a, w, plain, bias=bias, act=act, residual=r)
+    finally:
+        lib.splitk_enabled = was
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 2e-5
+    assert _rel(outs[0], ref) < tol
+    assert (outs[0].float() - ref).abs().max().item() < (0.15 if out_dtype == torch.bfloat16 else 1e-3)
+    # against the unsplit kernel: only the fp32 summation order of the tail tiles differs
+    d = (outs[0].float() - plain.float()).abs().max().item()
+    assert d < (0.07 if out_dtype == torch.bfloat16 else 2e-4), d
+    if out_dtype == torch.float32:
+        assert d > 0, "the split path did not run"  # (the fp32 summation order differs somewhere in the tail tiles)
+    ws = lib._SPLITK_WS[cuda_dev.index]
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0  # the counters are back to zero
+
+
 @pytest.mark.parametrize("split", [False, True])
 def test_gemm_grouped_conv_one_launch(cuda_dev, split):
     """HubertPositionalConvEmbedding-shaped grouped Conv1d (groups of 64 channels, zero padding k/2, + GELU + residual) as ONE
