@@ -546,22 +546,6 @@ def microbench(dev, args):
         sweep.append({"clips": n, "ms": ms, "GBps": alg / ms / 1e6, "frac": alg / ms / 1e6 / pk["hbm"]})
     vq["sweep_indices_and_zq"] = sweep
     del idx_t, idx_f
-    # ---- the BIWI latent width (D = 128, models/utils/config.py:44-60): 1024 clips x 6 s x 8 latent rows per frame ----
-    B2, L2, D2 = 1024, 149 * 8, 128
-    g2 = torch.Generator(device="cpu").manual_seed(7)
-    cb2 = (torch.randn(codes, D2, generator=g2) * 0.5).to(dev)
-    z2 = torch.randn(B2, L2, D2, device=dev)
-    d128 = {"rows": B2 * L2}
-    for name, algo, reps in (("tensor", lib.VQ_TENSOR, 10), ("ffma", lib.VQ_FFMA, 2)):
-        ms = timed(lambda i: lib.vq_quantize(z2, cb2, codes, want_bdl=True, algo=algo), reps, warm=1) / reps
-        alg = B2 * L2 * (8 * D2 + 8)
-        d128[name] = {"ms": ms, "achieved": alg / ms / 1e6, "unit": "GB/s", "peak": pk["hbm"], "frac": alg / ms / 1e6 / pk["hbm"],
-                      "bound": "hbm"}
-    i_t, _, _ = lib.vq_quantize(z2, cb2, codes, want_bdl=False, algo=lib.VQ_TENSOR)
-    i_f, _, _ = lib.vq_quantize(z2, cb2, codes, want_bdl=False, algo=lib.VQ_FFMA)
-    d128["tensor_equals_ffma_all_rows"] = bool(torch.equal(i_t, i_f))
-    vq["biwi_d128_indices_and_zq"] = d128
-    del z2, i_t, i_f
     # ---- through the public API: quant() (indices + z_q (B,D,L) + rows for the decoder + loss / perplexity by-products) ----
     lat = z[:batch]
     keep = []
@@ -578,6 +562,22 @@ def microbench(dev, args):
     out["vq_decode"] = {"ms": ms, "clips_per_s": clips / ms * 1e3, "achieved": fl / ms / 1e9, "unit": "TFLOP/s", "peak": pk["tf_sustained"],
                         "frac": fl / ms / 1e9 / pk["tf_sustained"], "bound": "tensor"}
     del z, keep
+    # ---- the BIWI latent width (D = 128, models/utils/config.py:44-60): 1024 clips x 6 s x 8 latent rows per frame ----
+    B2, L2, D2 = 1024, 149 * 8, 128
+    g2 = torch.Generator(device="cpu").manual_seed(7)
+    cb2 = (torch.randn(codes, D2, generator=g2) * 0.5).to(dev)
+    z2 = torch.randn(B2, L2, D2, device=dev)
+    d128 = {"rows": B2 * L2}
+    for name, algo, reps in (("tensor", lib.VQ_TENSOR, 10), ("ffma", lib.VQ_FFMA, 2)):
+        ms = timed(lambda i: lib.vq_quantize(z2, cb2, codes, want_bdl=True, algo=algo), reps, warm=1) / reps
+        alg = B2 * L2 * (8 * D2 + 8)
+        d128[name] = {"ms": ms, "achieved": alg / ms / 1e6, "unit": "GB/s", "peak": pk["hbm"], "frac": alg / ms / 1e6 / pk["hbm"],
+                      "bound": "hbm"}
+    i_t, _, _ = lib.vq_quantize(z2, cb2, codes, want_bdl=False, algo=lib.VQ_TENSOR)
+    i_f, _, _ = lib.vq_quantize(z2, cb2, codes, want_bdl=False, algo=lib.VQ_FFMA)
+    d128["tensor_equals_ffma_all_rows"] = bool(torch.equal(i_t, i_f))
+    out["vq_quantize"]["biwi_d128_indices_and_zq"] = d128
+    del z2, i_t, i_f
     # ---- HuBERT-large encode (bf16 throughput mode; and the split-bf16 mode the sampler uses by default) ----
     audios = [synthetic_audio(batch, n_samples, 0).to(dev) for _ in range(2)]
     fl = 383.1e9  # per clip at 10 s
