@@ -368,6 +368,29 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
   float* zzs = reinterpret_cast<float*>(smem + OFF_ZZ);
   uint32_t it = 0, hc = 0;
   const int row_q = tid >> 3, c8 = tid & 7;  // this thread's (row, 8-float column block) inside a 16-row slab
+  // (D = 128) address of this thread's unit 0 (row row_q, columns 64 h + 8 c8 ..) of sub-tile (tile, K-half), rows in the tile
+  auto unit0_of = [&](int tl2, int h2, int& nrows2) -> const float* {
+    const int b2 = tl2 / tpc;
+    const int64_t l2 = static_cast<int64_t>(tl2 - b2 * tpc) * TILE_ROWS;
+    nrows2 = static_cast<int>(min(static_cast<int64_t>(TILE_ROWS), L - l2));
+    return p.z + (static_cast<int64_t>(b2) * L + l2 + row_q) * D + h2 * 64 + c8 * 8;
+  };
+  float4 x0[8], x1[8];
+  if (!RING && cx.t_begin < t_end) {  // the first sub-tile's loads
+    int nr0;
+    const float* s0 = unit0_of(cx.t_begin, 0, nr0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (row_q + 16 * u < nr0) {
+        const float4* src = reinterpret_cast<const float4*>(s0 + static_cast<int64_t>(16 * u) * D);
+        x0[u] = __ldg(src);
+        x1[u] = __ldg(src + 1);
+      } else {
+        x0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[u] = x0[u];
+      }
+    }
+  }
   for (int tile = cx.t_begin; tile < t_end;) {
     int64_t off;
     const int seg_end = segment_begin(p, cx, tile, &off);
@@ -385,6 +408,7 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
         // All staged quarters of the tile are converted in one unrolled sweep (8 independent 8-float units per thread):
         // with one quarter at a time the four converter warps were latency-bound at ~950 cycles per quarter.
         const int nparts = (nrows + STG_ROWS - 1) / STG_ROWS;
+        float sqv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int part = 0; part < TILE_ROWS / STG_ROWS; ++part) {
           if (part < nparts) {
@@ -412,12 +436,21 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
               float sq = x0[q].x * x0[q].x;
               sq = fmaf(x0[q].y, x0[q].y, sq); sq = fmaf(x0[q].z, x0[q].z, sq); sq = fmaf(x0[q].w, x0[q].w, sq);
               sq = fmaf(x1[q].x, x1[q].x, sq); sq = fmaf(x1[q].y, x1[q].y, sq); sq = fmaf(x1[q].z, x1[q].z, sq); sq = fmaf(x1[q].w, x1[q].w, sq);
-              sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-              sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-              sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-              if (c8 == 0) zz[arow] = sq;
+              sqv[part * 2 + q] = sq;
             }
           }
+        }
+        // the eight row sums' butterfly rounds back to back: within a round the shuffles are independent, so the warp does not
+        // sit out a shuffle latency per unit (D = 128 converter: 0.38 -> 0.31 ms for 1.22 M rows with the same change)
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sqv[u] += __shfl_xor_sync(0xffffffffu, sqv[u], o);
+        }
+        if (c8 == 0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if ((u >> 1) < nparts) zz[(u >> 1) * STG_ROWS + row_q + 16 * (u & 1)] = sqv[u];
         }
         hc += nparts;
         fence_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
@@ -425,9 +458,14 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
         if (lane == 0) mbar_arrive(bar_a_full(base, as));
         TRACE(2);
       } else {
-        // ---- no staging ring (D = 128): global -> registers -> (hi, lo) A stage, one K-half at a time ----
-        const float* const zrow0 = p.z + (static_cast<int64_t>(b) * L + l0) * D;
-        if (tid == 0) {  // pull the tiles ahead into L2 (the loads below then hit L2)
+        // ---- no staging ring (D = 128): global -> registers -> (hi, lo) A stage, one K-half at a time. The registers hold
+        //      the sub-tile being converted; as soon as a unit has been consumed its registers receive the same unit of the
+        //      NEXT sub-tile, so 16 x 16 bytes per thread stay in flight through the whole conversion. (The converters are the
+        //      bottleneck of this variant: ~3k cycles per K-half, a 600-instruction dependent sequence on one warp per
+        //      scheduler - ncu: 19 % issue slots, the rest fixed-latency and shuffle waits. Two converter groups - 576
+        //      threads, 96 registers - were tried on alternate K-halves and on alternate tiles: 0.35-0.37 ms against 0.38 ms
+        //      for 1.22 M rows, not worth the second producer protocol.) ----
+        if (tid == 0) {  // pull the tiles ahead into L2 (the loads then hit L2)
           const int ahead = p.l2_ahead;
           const int first = (tl == cx.t_begin) ? tl + 1 : tl + ahead;
           for (int ta = first; ta <= tl + ahead && ta < t_end; ++ta) {
@@ -441,23 +479,16 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
         for (int h = 0; h < KH; ++h) {
           const uint32_t sit = it * KH + h;
           const int as = sit & 1;
-          float4 x0[8], x1[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {  // rows row_q + 16 u; eight lanes cover the 256 contiguous bytes of a row's K-half
-            const int row = row_q + 16 * u;
-            if (row < nrows) {
-              const float4* src = reinterpret_cast<const float4*>(zrow0 + static_cast<int64_t>(row) * D + h * 64 + c8 * 8);
-              x0[u] = __ldg(src);
-              x1[u] = __ldg(src + 1);
-            } else {
-              x0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              x1[u] = x0[u];
-            }
-          }
-          TRACE(0);
+          // the sub-tile after this one: the other K-half, or the first K-half of the next tile
+          const int ntl = (h + 1 < KH) ? tl : tl + 1, nh = (h + 1 < KH) ? h + 1 : 0;
+          int nnr = 0;
+          const float* nsrc = nullptr;
+          if (ntl < t_end) nsrc = unit0_of(ntl, nh, nnr);
+          TRACE(h == KH - 1 ? 0 : 13);
           mbar_wait(bar_a_empty(base, as), ((sit >> 1) & 1u) ^ 1u);
-          TRACE(1);
+          TRACE(h == KH - 1 ? 1 : 14);
           const uint32_t a_hi = base + OFF_A + as * A_STAGE_BYTES, a_lo = a_hi + A_OP_BYTES;
+          float sq[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int row = row_q + 16 * u;
@@ -466,18 +497,33 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
             const uint32_t o = static_cast<uint32_t>(row * 128 + ((c8 ^ (row & 7)) << 4));
             st_shared_v4(a_hi + o, hi);
             st_shared_v4(a_lo + o, lo);
-            float sq = x0[u].x * x0[u].x;
-            sq = fmaf(x0[u].y, x0[u].y, sq); sq = fmaf(x0[u].z, x0[u].z, sq); sq = fmaf(x0[u].w, x0[u].w, sq);
-            sq = fmaf(x1[u].x, x1[u].x, sq); sq = fmaf(x1[u].y, x1[u].y, sq); sq = fmaf(x1[u].z, x1[u].z, sq); sq = fmaf(x1[u].w, x1[u].w, sq);
-            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-            if (c8 == 0) zz[row] = (h == 0) ? sq : zz[row] + sq;  // the same thread owns (row, c8 = 0) in every K-half
+            float q = x0[u].x * x0[u].x;
+            q = fmaf(x0[u].y, x0[u].y, q); q = fmaf(x0[u].z, x0[u].z, q); q = fmaf(x0[u].w, x0[u].w, q);
+            q = fmaf(x1[u].x, x1[u].x, q); q = fmaf(x1[u].y, x1[u].y, q); q = fmaf(x1[u].z, x1[u].z, q); q = fmaf(x1[u].w, x1[u].w, q);
+            sq[u] = q;
+            if (row < nnr) {  // (nnr = 0 when there is no next sub-tile)
+              const float4* src = reinterpret_cast<const float4*>(nsrc + static_cast<int64_t>(16 * u) * D);
+              x0[u] = __ldg(src);
+              x1[u] = __ldg(src + 1);
+            } else {
+              x0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              x1[u] = x0[u];
+            }
+          }
+          // the eight row sums' butterfly rounds back to back (each round's shuffles are independent of one another)
+#pragma unroll
+          for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
+          }
+          if (c8 == 0) {  // the same thread owns (row, c8 = 0) in both K-halves
+#pragma unroll
+            for (int u = 0; u < 8; ++u) zz[row_q + 16 * u] = (h == 0) ? sq[u] : zz[row_q + 16 * u] + sq[u];
           }
           fence_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_full(base, as));
-          TRACE(2);
+          TRACE(h == KH - 1 ? 2 : 15);
         }
       }
     }
