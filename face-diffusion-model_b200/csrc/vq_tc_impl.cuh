@@ -28,8 +28,10 @@
 //     (Tracking (max, second max, index) with min/max/select was ALU-pipe-bound; two sweeps were TMEM-bound.)
 // Rows containing +-Inf / NaN (|z|^2 not finite) always take the exact pass and come out as code 0, like the oracle.
 // Pipeline of one persistent CTA (448 threads, 1 CTA / SM, contiguous range of 128-row tiles):
-//   warp 8      cp.async.bulk (1-D TMA) of fp32 z quarter-tiles (32 rows = 8 KB) into a 9-deep ring (72 KB in flight)
-//   warps 10-13 fp32 -> (hi, lo) bf16 in the 128B-swizzled K-major A-operand layout, |z|^2 estimate per row
+//   warps 10-13 fp32 rows from global memory (L2 hits: cp.async.bulk.prefetch.L2 two tiles ahead; the next tile's 16-byte units
+//               are loaded into the registers as the current ones are consumed) -> (hi, lo) bf16 in the 128B-swizzled K-major
+//               A-operand layout, |z|^2 estimate per row
+//   warp 8      idle (it fed a shared-memory staging ring with 1-D TMA copies in the first version: -DVQ_RING64=1)
 //   warp 9      13 x tcgen05.mma (128 x 256 x 16) per tile into one of two 256-column TMEM accumulators
 //   warps 0-7   two epilogue groups (one per accumulator): tcgen05.ld, pass A / pass B over the scores, recheck,
 //               int64 index, gather of the winning code row into z_q (B, D, L) and / or (B, L, D)
@@ -45,7 +47,14 @@ namespace VQ_NS {
 
 constexpr int D = VQ_D;
 constexpr int KH = D / 64;                    // 64-dimension K-halves per row (one A stage each)
-constexpr bool RING = (D == 64);              // fp32 staging ring fed by 1-D TMA (D = 64 only)
+// The first D = 64 kernel staged the fp32 rows through a 9-deep shared-memory ring fed by 1-D TMA copies (warp 8) and converted
+// them from there; reading global memory directly with the register prefetch below is faster (8.16 M rows: indices 1.03 -> 0.90 ms,
+// with z_q 1.26 -> 1.24 ms, A/B on one box) because the converter warps, not the loads, set the pace and the ring added a barrier
+// wait and a shared-memory round trip per 32 rows. -DVQ_RING64=1 builds the ring variant (D = 64 only) for comparison.
+#ifndef VQ_RING64
+#define VQ_RING64 0
+#endif
+constexpr bool RING = (D == 64) && VQ_RING64;
 constexpr int TILE_ROWS = 128;
 constexpr int STG_ROWS = 32;
 constexpr int STG_STAGES = RING ? 9 : 1;       // (D = 128: no ring; one dummy barrier pair)
