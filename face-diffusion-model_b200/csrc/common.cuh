@@ -89,6 +89,22 @@ __device__ __forceinline__ float act_mish(float x) {
   return x * (n / (n + 2.f));
 }
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU for outputs that are rounded to bf16 (bf16 GEMM epilogues, the bf16 path of the HuBERT conv0 kernel; fp32 outputs keep erff):
+// no MUFU at all. erf(x / sqrt 2) = w P(w^2) with w = clamp(x / (2 R sqrt 2), -1/2, 1/2), R = 2.85, P of degree 7 fitted on
+// Chebyshev nodes with P(1/4) / 2 = 1 pinned, so beyond |x| = 4.03 the result is exactly x or 0. |GELU error| < 1.3e-4
+// (at |x| ~ 4, where a bf16 ulp is 1.6e-2); 13 FMA-pipe instructions per element against ~22 + 2 MUFU.
+__device__ __forceinline__ float act_gelu_erf_poly(float x) {
+  const float w = __saturatef(fmaf(x, 0.12405407f, 0.5f)) - 0.5f;  // 1 / (2 * 2.85 * sqrt 2)
+  const float s = w * w;
+  float p = fmaf(-108514.76f, s, 133392.03f);
+  p = fmaf(p, s, -71527.083f);
+  p = fmaf(p, s, 22276.801f);
+  p = fmaf(p, s, -4549.4910f);
+  p = fmaf(p, s, 653.65449f);
+  p = fmaf(p, s, -69.234234f);
+  p = fmaf(p, s, 6.4296663f);
+  return x * fmaf(0.5f, w * p, 0.5f);
+}
 __device__ __forceinline__ float act_gelu_tanh(float x) {
   // models/utils/base_model_util.py:81-94
   float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);

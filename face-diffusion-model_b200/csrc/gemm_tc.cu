@@ -108,23 +108,9 @@ __device__ __forceinline__ float act_gelu_erf_fast(float x) {
   const float erf_abs = 1.f - p * t * __expf(-z * z);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
-// erf-GELU for outputs that are rounded to bf16 (plain bf16 GEMMs only: fp32 / split-bf16 outputs keep the 1.5e-7 form above):
-// no MUFU at all. erf(x / sqrt 2) = w P(w^2) with w = clamp(x / (2 R sqrt 2), -1/2, 1/2), R = 2.85, P of degree 7 fitted on
-// Chebyshev nodes with P(1/4) / 2 = 1 pinned, so beyond |x| = 4.03 the result is exactly x or 0. |GELU error| < 1.3e-4
-// (at |x| ~ 4, where a bf16 ulp is 1.6e-2); 13 FMA-pipe instructions per element against ~22 + 2 MUFU: HuBERT's FFN1
-// GEMMs (N = 4096, K = 1024) had their epilogue, not the MMAs, on the critical path (584 vs 813 TFLOP/s for the QKV GEMM).
-__device__ __forceinline__ float act_gelu_erf_poly(float x) {
-  const float w = __saturatef(fmaf(x, 0.12405407f, 0.5f)) - 0.5f;  // 1 / (2 * 2.85 * sqrt 2)
-  const float s = w * w;
-  float p = fmaf(-108514.76f, s, 133392.03f);
-  p = fmaf(p, s, -71527.083f);
-  p = fmaf(p, s, 22276.801f);
-  p = fmaf(p, s, -4549.4910f);
-  p = fmaf(p, s, 653.65449f);
-  p = fmaf(p, s, -69.234234f);
-  p = fmaf(p, s, 6.4296663f);
-  return x * fmaf(0.5f, w * p, 0.5f);
-}
+// act_gelu_erf_poly (common.cuh): the MUFU-free erf-GELU for outputs that are rounded to bf16 (plain bf16 GEMMs only; fp32 /
+// split-bf16 outputs keep the 1.5e-7 form above). HuBERT's FFN1 GEMMs (N = 4096, K = 1024) had their epilogue, not the MMAs, on
+// the critical path (584 vs 813 TFLOP/s for the QKV GEMM).
 constexpr int ACT_GELU_ERF_BF16 = 100;  // internal: FDM_ACT_GELU_ERF of a plain bf16-output GEMM
 __device__ __forceinline__ void act_inplace(float (&v)[32], int act) {
   if (act == FDM_ACT_NONE) return;

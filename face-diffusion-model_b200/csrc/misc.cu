@@ -1,6 +1,7 @@
 // Small data-movement kernels around the GEMMs: casts, the (B,C,L)->(B,L,C) transpose of VQAutoEncoder.decode,
 // per-clip time padding for the implicit convolutions, and HuBERT's first conv layer (1 input channel).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -128,6 +129,131 @@ __global__ void __launch_bounds__(256) hubert_conv0_kernel(const float* __restri
   for (int j = 0; j < CPL; ++j) {
     const int c = lane + 32 * j;
     st_from_float(out, od, orow + c, act_gelu_erf((v[j] - mean) * rstd * g[c] + beta[c]));
+  }
+}
+
+// C = 512 (hubert-large / wav2vec2-base first layer). The kernel above reads every weight from shared memory once per
+// frame (160 two-way-conflicting LDS.32 against 160 FMAs per lane: 1.08 ms for 64 clips x 4 s, 14 % of the FFMA rate).
+// Here a warp computes FOUR consecutive frames per pass from k-major float4 weights (one conflict-free LDS.128 feeds 16
+// FMAs), a lane owns channels 128 j + 4 lane .. + 3 (8- / 16-byte output stores, 256 / 512 contiguous bytes per warp), the
+// four frames' LayerNorm reductions are interleaved, and bf16 outputs take the polynomial erf-GELU.
+constexpr int C0_FRAMES = 4;       // frames per warp pass
+constexpr int C0_PASSES = 4;       // passes per warp: a CTA of 8 warps covers 128 frames per weight load
+__global__ void __launch_bounds__(256) hubert_conv0_c512_kernel(const float* __restrict__ audio, int64_t L, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ g,
+                                                                const float* __restrict__ beta, void* out, int od, int Lout,
+                                                                int64_t out_t_stride) {
+  constexpr int C = 512;
+  __shared__ float4 ws4[10 * 4 * 32];  // [k][j][lane] = w[128 j + 4 lane + 0..3][k]
+  __shared__ float4 pb4[3 * 4 * 32];   // bias, gamma, beta in the same channel order
+  for (int i = threadIdx.x; i < 10 * 4 * 32; i += blockDim.x) {
+    const int k = i / 128, c = 4 * (i % 128);  // (j, lane) -> channel 128 j + 4 lane = 4 (i % 128)
+    ws4[i] = make_float4(w[(c + 0) * 10 + k], w[(c + 1) * 10 + k], w[(c + 2) * 10 + k], w[(c + 3) * 10 + k]);
+  }
+  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
+    const int which = i / 128, c = 4 * (i % 128);
+    const float* src = which == 0 ? bias : (which == 1 ? g : beta);
+    pb4[i] = src ? make_float4(src[c], src[c + 1], src[c + 2], src[c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.y;
+  const float* a = audio + b * L;
+  const bool bf = od == FDM_BF16;
+#pragma unroll 1
+  for (int pass = 0; pass < C0_PASSES; ++pass) {
+    const int64_t t0 = (static_cast<int64_t>(blockIdx.x) * C0_PASSES + pass) * (8 * C0_FRAMES) + warp * C0_FRAMES;
+    if (t0 >= out_t_stride) return;
+    float x[5 * (C0_FRAMES - 1) + 10];
+#pragma unroll
+    for (int i = 0; i < 5 * (C0_FRAMES - 1) + 10; ++i) {
+      const int64_t si = t0 * 5 + i;
+      x[i] = __ldg(a + (si < L ? si : L - 1));  // (frames >= Lout are masked below)
+    }
+    float acc[C0_FRAMES][16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = pb4[j * 32 + lane];
+#pragma unroll
+      for (int f = 0; f < C0_FRAMES; ++f) { acc[f][4 * j] = b4.x; acc[f][4 * j + 1] = b4.y; acc[f][4 * j + 2] = b4.z; acc[f][4 * j + 3] = b4.w; }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = ws4[(k * 4 + j) * 32 + lane];
+#pragma unroll
+        for (int f = 0; f < C0_FRAMES; ++f) {
+          const float xv = x[5 * f + k];
+          acc[f][4 * j] = fmaf(w4.x, xv, acc[f][4 * j]);
+          acc[f][4 * j + 1] = fmaf(w4.y, xv, acc[f][4 * j + 1]);
+          acc[f][4 * j + 2] = fmaf(w4.z, xv, acc[f][4 * j + 2]);
+          acc[f][4 * j + 3] = fmaf(w4.w, xv, acc[f][4 * j + 3]);
+        }
+      }
+    }
+    float mean[C0_FRAMES], rstd[C0_FRAMES];
+    if (g != nullptr) {  // LayerNorm over the 512 channels of each frame: the four frames' butterflies interleaved
+      float s[C0_FRAMES], q[C0_FRAMES];
+#pragma unroll
+      for (int f = 0; f < C0_FRAMES; ++f) {
+        s[f] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s[f] += acc[f][i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int f = 0; f < C0_FRAMES; ++f) s[f] += __shfl_xor_sync(0xffffffffu, s[f], o);
+      }
+#pragma unroll
+      for (int f = 0; f < C0_FRAMES; ++f) {
+        mean[f] = s[f] * (1.f / C);
+        q[f] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) q[f] = fmaf(acc[f][i] - mean[f], acc[f][i] - mean[f], q[f]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int f = 0; f < C0_FRAMES; ++f) q[f] += __shfl_xor_sync(0xffffffffu, q[f], o);
+      }
+#pragma unroll
+      for (int f = 0; f < C0_FRAMES; ++f) rstd[f] = 1.f / sqrtf(q[f] * (1.f / C) + 1e-5f);
+    }
+#pragma unroll
+    for (int f = 0; f < C0_FRAMES; ++f) {
+      const int64_t t = t0 + f;
+      if (t >= out_t_stride) break;
+      const bool live = t < Lout;  // padding frames of the per-clip stride stay zero
+      const int64_t orow = (b * out_t_stride + t) * C;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = acc[f][4 * j + i];
+        if (g != nullptr) {
+          const float4 g4 = pb4[(4 + j) * 32 + lane], e4 = pb4[(8 + j) * 32 + lane];
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float y = fmaf((o[i] - mean[f]) * rstd[f], gg[i], ee[i]);
+            o[i] = bf ? act_gelu_erf_poly(y) : act_gelu_erf(y);
+          }
+        }
+        if (!live) { o[0] = o[1] = o[2] = o[3] = 0.f; }
+        const int64_t oi = orow + 128 * j + 4 * lane;
+        if (bf) {
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+          uint2 v;
+          v.x = *reinterpret_cast<const uint32_t*>(&p0);
+          v.y = *reinterpret_cast<const uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + oi) = v;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + oi) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
   }
 }
 
@@ -351,7 +477,12 @@ extern "C" int fdm_hubert_conv0(const float* audio, int64_t B, int64_t L, const 
   FDM_CHECK_ARG(B > 0 && B <= 65535 && Lout > 0 && out_t_stride >= Lout && (Lout - 1) * 5 + 10 <= L, "fdm_hubert_conv0: bad sizes");
   dim3 grid(static_cast<unsigned>(ceil_div64(out_t_stride, 8)), static_cast<unsigned>(B));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (C == 512) hubert_conv0_kernel<16><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
+  static const bool c512_fast = [] { const char* e = getenv("FDM_B200_CONV0_FAST"); return !(e && e[0] == '0'); }();
+  const int64_t esz = out_dtype == FDM_BF16 ? 2 : 4;
+  if (C == 512 && c512_fast && reinterpret_cast<uintptr_t>(out) % 16 == 0 && (out_t_stride * C * esz) % 16 == 0) {
+    dim3 grid4(static_cast<unsigned>(ceil_div64(out_t_stride, 8 * C0_FRAMES * C0_PASSES)), static_cast<unsigned>(B));
+    hubert_conv0_c512_kernel<<<grid4, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
+  } else if (C == 512) hubert_conv0_kernel<16><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
   else if (C == 32) hubert_conv0_kernel<1><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
   else if (C == 64) hubert_conv0_kernel<2><<<grid, 256, 0, s>>>(audio, L, w, bias, ln_g, ln_b, out, out_dtype, static_cast<int>(Lout), out_t_stride);
   else FDM_CHECK_ARG(false, "fdm_hubert_conv0: C=%lld not in {32,64,512}", (long long)C);

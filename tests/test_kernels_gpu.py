@@ -698,6 +698,20 @@ def test_misc_kernels(cuda_dev):
     torch.cuda.synchronize()
     assert _rel(out[:, :Lout], ref) < 1e-5
     assert (out[:, Lout:] == 0).all()
+    # bf16 output (polynomial erf-GELU), a per-clip stride that is not a multiple of the 128 frames a CTA covers, and the raw
+    # variant without LayerNorm (wav2vec2-base: GroupNorm over time follows in another kernel)
+    for stride in (800, 803):
+        ob = torch.full((2, stride, 512), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+        lib.hubert_conv0(audio, w.view(512, 10).contiguous(), b, lg, lb, ob, Lout, stride, 512)
+        torch.cuda.synchronize()
+        assert _rel(ob[:, :Lout], ref) < 4e-3
+        assert (ob[:, :Lout].float() - ref).abs().max().item() < 2e-4 + 2.0 ** -8 * ref.abs().max().item()
+        assert (ob[:, Lout:] == 0).all()
+    raw = torch.full((2, 800, 512), float("nan"), device=cuda_dev)
+    lib.hubert_conv0(audio, w.view(512, 10).contiguous(), None, None, None, raw, Lout, 800, 512)
+    torch.cuda.synchronize()
+    assert _rel(raw[:, :Lout], F.conv1d(audio[:, None], w, None, stride=5).transpose(1, 2)) < 1e-5
+    assert (raw[:, Lout:] == 0).all()
 
 
 @pytest.mark.parametrize("orig_sr", [44100, 48000, 22050, 8000])
