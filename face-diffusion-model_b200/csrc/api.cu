@@ -15,7 +15,7 @@ void fdm_set_error(const char* fmt, ...) {
 
 extern "C" const char* fdm_last_error(void) { return g_err; }
 
-extern "C" int fdm_abi_version(void) { return 3; }  // 3: split-bf16 GEMM operands, fdm_ddpm_args.seed_dev, fdm_split_bf16x2
+extern "C" int fdm_abi_version(void) { return 4; }  // 3: split-bf16 GEMM operands, fdm_ddpm_args.seed_dev, fdm_split_bf16x2; 4: fdm_gemm_args.a_group_cols / splitk_ws, tensor-core VQ for D = 128
 
 int fdm_sm_count() {
   static int cached[64] = {0};

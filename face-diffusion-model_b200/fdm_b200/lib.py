@@ -93,6 +93,9 @@ class FdmError(RuntimeError):
     pass
 
 
+ABI_VERSION = 4  # fdm_abi_version() of the library these ctypes structs mirror
+
+
 def load() -> C.CDLL:
     """dlopen the library and bind every symbol include/fdm_b200.h declares (no GPU needed)."""
     global _lib
@@ -104,6 +107,9 @@ def load() -> C.CDLL:
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
+        if lib.fdm_abi_version() != ABI_VERSION:  # a stale build would read the argument structs with another layout
+            raise FdmError(f"{LIB_PATH} has ABI version {lib.fdm_abi_version()}, this binding needs {ABI_VERSION}: rebuild it "
+                           "(`python -c 'import __graft_entry__ as g; g.build()'`)")
         _lib = lib
     return _lib
 

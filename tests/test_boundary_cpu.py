@@ -84,7 +84,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/fdm_b200.h but not exported"
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
-    assert handle.fdm_abi_version() == 3
+    assert handle.fdm_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
