@@ -759,7 +759,12 @@ __device__ __noinline__ void role_epilogue(const Params& p, const Ctx& cx) {
       const float w = window * 1.0001f;  // codes with a_j < max - w cannot be the arg-min of d
       const float big = 1.152921504606846976e18f;  // 2^60
       float M1 = -INFINITY;
-      float S[4] = {0.f, 0.f, 0.f, 0.f}, J[4] = {0.f, 0.f, 0.f, 0.f};
+      // Count and index of the codes inside the window ride in ONE accumulator per chunk: T = sum ind_j (j + 1024) over the
+      // chunk's 32 codes (ind_j in {0, 1}: T = 1024 n + sum of the n candidates' local indices, exact in fp32, sum j <= 496),
+      // so the per-code work is FFMA.SAT + FFMA (+ half an FMNMX) instead of FFMA.SAT + FADD + FFMA, and n = floor(T / 1024)
+      // is taken once per chunk. A fractional ind (a_j within 2^-60 of the threshold) leaves T, hence J, fractional: such rows
+      // are flagged like the rows with S != 1.
+      float S = 0.f, J = 0.f;
       uint32_t cmask = 0u;
       auto scan_chunk = [&](const uint32_t (&r)[32], int c) {
         float cm[4];
@@ -771,23 +776,23 @@ __device__ __noinline__ void role_epilogue(const Params& p, const Ctx& cx) {
           for (int t = 0; t < 4; ++t) cm[t] = fmax3(cm[t], __uint_as_float(r[8 * q + t]), __uint_as_float(r[8 * q + 4 + t]));
         const float Mn = fmaxf(M1, fmax3(fmaxf(cm[0], cm[1]), cm[2], cm[3]));
         if (Mn - M1 > w) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) { S[t] = 0.f; J[t] = 0.f; }
+          S = 0.f;
+          J = 0.f;
           cmask = 0u;
         }
         M1 = Mn;
         const float cc = -(M1 - w) * big;
-        float sc[4] = {0.f, 0.f, 0.f, 0.f}, jc[4] = {0.f, 0.f, 0.f, 0.f};
+        float tc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float ind = __saturatef(fmaf(__uint_as_float(r[j]), big, cc));
-          sc[j & 3] += ind;
-          jc[j & 3] = fmaf(ind, static_cast<float>(j), jc[j & 3]);
+          tc[j & 3] = fmaf(ind, static_cast<float>(j + 1024), tc[j & 3]);
         }
-        const float base_j = static_cast<float>(c * 32);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) { S[t] += sc[t]; J[t] += fmaf(sc[t], base_j, jc[t]); }
-        if ((sc[0] + sc[1]) + (sc[2] + sc[3]) > 0.f) cmask |= 1u << c;  // chunks that hold codes inside the window
+        const float tl = (tc[0] + tc[1]) + (tc[2] + tc[3]);
+        const float cnt = floorf(tl * 0.0009765625f);  // codes of this chunk inside the window
+        S += cnt;
+        J += fmaf(cnt, static_cast<float>(c * 32 - 1024), tl);  // + sum of their global indices
+        if (tl > 0.f) cmask |= 1u << c;  // chunks that hold codes inside the window
       };
 #pragma unroll 1
       for (int c = 0; c < nchunks; c += 2) {  // two chunks per TMEM round trip (the round trip, not the bandwidth, costs)
@@ -800,8 +805,9 @@ __device__ __noinline__ void role_epilogue(const Params& p, const Ctx& cx) {
       }
       const float thr = M1 - w;
       if (quad == 0) TRACE(9);
-      const float Ssum = (S[0] + S[1]) + (S[2] + S[3]);
-      int idx = static_cast<int>((J[0] + J[1]) + (J[2] + J[3]) + 0.5f);
+      // exactly one whole candidate: S == 1 and J an integer (a second code with a fractional ind would show up in J)
+      const float Ssum = (J == rintf(J)) ? S : 2.f;
+      int idx = static_cast<int>(J + 0.5f);
       // a row whose |z|^2 is +Inf / NaN has no finite distance: the oracle's strict '<' from +Inf keeps index 0. Its scores
       // are Inf / NaN mixtures that could fake S == 1, so such rows always take the exact pass (empty candidate masks -> 0).
       const bool nonfinite = !(zzr < INFINITY);
