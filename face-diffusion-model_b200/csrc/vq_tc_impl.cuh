@@ -69,8 +69,14 @@ constexpr int AUG_LBO = 128, AUG_SBO = 256;   // k-chunk stride, 8-row group str
 constexpr int ZZ_SLOTS = 4;
 constexpr int L2_AHEAD = 2;  // tiles prefetched into L2 ahead of the shared-memory ring (8 tiles = 38 MB chip-wide were partly evicted before
                              // use: ncu DRAM reads 2.51 GB for 2.09 GB of latents; 2 tiles: 2.09 GB, same speed)
-constexpr int NUM_THREADS = 448;
-constexpr int CONV_THREADS = 128;
+#ifndef VQ_CONV_WARPS
+#define VQ_CONV_WARPS 4
+#endif
+constexpr int CONV_THREADS = VQ_CONV_WARPS * 32;  // 4 (448 threads, 128 registers) or 8 converter warps (576 threads, 96 registers)
+constexpr int CONV_RPP = CONV_THREADS / 8;           // rows per pass of the converter group (8 threads per row)
+constexpr int CONV_UNITS = TILE_ROWS / CONV_RPP;     // 8-float units per thread and K-half
+static_assert(!RING || VQ_CONV_WARPS == 4, "the ring variant is written for four converter warps");
+constexpr int NUM_THREADS = 320 + CONV_THREADS;
 // Warp roles. The SMSP arbiter prefers the HIGHEST warp id among eligible warps, so the converters - the head of the
 // pipeline, one warp per scheduler - get the top ids; with ids 0-3 they only issued when both epilogue warps of their
 // scheduler were stalled and took ~4k cycles per tile.
@@ -384,14 +390,14 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
     nrows2 = static_cast<int>(min(static_cast<int64_t>(TILE_ROWS), L - l2));
     return p.z + (static_cast<int64_t>(b2) * L + l2 + row_q) * D + h2 * 64 + c8 * 8;
   };
-  float4 x0[8], x1[8];
+  float4 x0[CONV_UNITS], x1[CONV_UNITS];
   if (!RING && cx.t_begin < t_end) {  // the first sub-tile's loads
     int nr0;
     const float* s0 = unit0_of(cx.t_begin, 0, nr0);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (row_q + 16 * u < nr0) {
-        const float4* src = reinterpret_cast<const float4*>(s0 + static_cast<int64_t>(16 * u) * D);
+    for (int u = 0; u < CONV_UNITS; ++u) {
+      if (row_q + CONV_RPP * u < nr0) {
+        const float4* src = reinterpret_cast<const float4*>(s0 + static_cast<int64_t>(CONV_RPP * u) * D);
         x0[u] = __ldg(src);
         x1[u] = __ldg(src + 1);
       } else {
@@ -497,10 +503,10 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
           mbar_wait(bar_a_empty(base, as), ((sit >> 1) & 1u) ^ 1u);
           TRACE(h == KH - 1 ? 1 : 14);
           const uint32_t a_hi = base + OFF_A + as * A_STAGE_BYTES, a_lo = a_hi + A_OP_BYTES;
-          float sq[8];
+          float sq[CONV_UNITS];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int row = row_q + 16 * u;
+          for (int u = 0; u < CONV_UNITS; ++u) {
+            const int row = row_q + CONV_RPP * u;
             uint4 hi, lo;
             split8(x0[u], x1[u], hi, lo);
             const uint32_t o = static_cast<uint32_t>(row * 128 + ((c8 ^ (row & 7)) << 4));
@@ -511,7 +517,7 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
             q = fmaf(x1[u].x, x1[u].x, q); q = fmaf(x1[u].y, x1[u].y, q); q = fmaf(x1[u].z, x1[u].z, q); q = fmaf(x1[u].w, x1[u].w, q);
             sq[u] = q;
             if (row < nnr) {  // (nnr = 0 when there is no next sub-tile)
-              const float4* src = reinterpret_cast<const float4*>(nsrc + static_cast<int64_t>(16 * u) * D);
+              const float4* src = reinterpret_cast<const float4*>(nsrc + static_cast<int64_t>(CONV_RPP * u) * D);
               x0[u] = __ldg(src);
               x1[u] = __ldg(src + 1);
             } else {
@@ -523,11 +529,11 @@ __device__ __noinline__ void role_convert(const Params& p, const Ctx& cx) {
 #pragma unroll
           for (int o = 1; o <= 4; o <<= 1) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
+            for (int u = 0; u < CONV_UNITS; ++u) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
           }
           if (c8 == 0) {  // the same thread owns (row, c8 = 0) in both K-halves
 #pragma unroll
-            for (int u = 0; u < 8; ++u) zz[row_q + 16 * u] = (h == 0) ? sq[u] : zz[row_q + 16 * u] + sq[u];
+            for (int u = 0; u < CONV_UNITS; ++u) zz[row_q + CONV_RPP * u] = (h == 0) ? sq[u] : zz[row_q + CONV_RPP * u] + sq[u];
           }
           fence_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
           __syncwarp();
@@ -794,14 +800,24 @@ __device__ __noinline__ void role_epilogue(const Params& p, const Ctx& cx) {
         J += fmaf(cnt, static_cast<float>(c * 32 - 1024), tl);  // + sum of their global indices
         if (tl > 0.f) cmask |= 1u << c;  // chunks that hold codes inside the window
       };
+      if (VQ_CONV_WARPS == 4) {
 #pragma unroll 1
-      for (int c = 0; c < nchunks; c += 2) {  // two chunks per TMEM round trip (the round trip, not the bandwidth, costs)
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32b_x32(tacc + c * 32, ra);
-        if (c + 1 < nchunks) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, rb);
-        tmem_ld_wait();
-        scan_chunk(ra, c);
-        if (c + 1 < nchunks) scan_chunk(rb, c + 1);
+        for (int c = 0; c < nchunks; c += 2) {  // two chunks per TMEM round trip (the round trip, not the bandwidth, costs)
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32b_x32(tacc + c * 32, ra);
+          if (c + 1 < nchunks) tmem_ld_32x32b_x32(tacc + (c + 1) * 32, rb);
+          tmem_ld_wait();
+          scan_chunk(ra, c);
+          if (c + 1 < nchunks) scan_chunk(rb, c + 1);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {  // (96 registers per thread: one chunk in flight)
+          uint32_t ra[32];
+          tmem_ld_32x32b_x32(tacc + c * 32, ra);
+          tmem_ld_wait();
+          scan_chunk(ra, c);
+        }
       }
       const float thr = M1 - w;
       if (quad == 0) TRACE(9);
