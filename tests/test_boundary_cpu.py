@@ -169,3 +169,41 @@ def test_resample_filter_matches_scipy_design():
         n_pre_pad = down - half_len % down
         assert np.abs(taps.numpy() - np.concatenate([np.zeros(n_pre_pad), h])).max() < 1e-14
         assert pre == (half_len + n_pre_pad) // down
+
+
+def test_binding_refuses_a_library_with_another_abi_version(monkeypatch):
+    """A stale libfdm_b200.so would read the ctypes argument structs with another layout: load() must refuse it."""
+    from fdm_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "ABI_VERSION", lib.ABI_VERSION + 1)
+    with pytest.raises(lib.FdmError, match="ABI version"):
+        lib.load()
+    monkeypatch.setattr(lib, "ABI_VERSION", lib.ABI_VERSION - 1)
+    assert lib.load().fdm_abi_version() == lib.ABI_VERSION
+
+
+def test_polynomial_erf_gelu_constants():
+    """The MUFU-free erf-GELU of the bf16 epilogues (csrc/common.cuh: act_gelu_erf_poly), restated in float32 numpy from the
+    constants in the source: |error| < 1.3e-4 against the exact GELU everywhere, exactly x (1 + O(1e-6)) / x O(1e-6) beyond the clamp."""
+    import re
+    import numpy as np
+    from scipy.special import erf
+    src = open(os.path.join(ROOT, "face-diffusion-model_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float act_gelu_erf_poly(float x)"):]
+    body = body[:body.index("}") + 1]
+    scale = np.float32(re.search(r"fmaf\(x, ([0-9.eE+-]+)f, 0\.5f\)", body).group(1))
+    first = re.search(r"fmaf\((-?[0-9.]+)f, s, (-?[0-9.]+)f\)", body)
+    chain = [np.float32(first.group(1)), np.float32(first.group(2))] + [np.float32(c) for c in re.findall(r"p = fmaf\(p, s, (-?[0-9.]+)f\)", body)]
+    assert len(chain) == 8, chain
+    x = np.linspace(-12, 12, 480001).astype(np.float32)
+    w = (np.clip(x * scale + np.float32(0.5), 0, 1) - np.float32(0.5)).astype(np.float32)
+    s2 = (w * w).astype(np.float32)
+    p = np.full_like(s2, chain[0])
+    for c in chain[1:]:
+        p = (p * s2 + c).astype(np.float32)
+    y = (x * (np.float32(0.5) * (w * p).astype(np.float32) + np.float32(0.5))).astype(np.float32)
+    ref = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(y - ref).max() < 1.3e-4
+    far = np.abs(x) > 4.1
+    assert np.abs(y[far] - ref[far]).max() < 2e-5 * 12
+    assert abs(float(scale) - 1 / (2 * 2.85 * np.sqrt(2))) < 1e-6
