@@ -1,7 +1,6 @@
 // fdm_vq_quantize, tensor-core path: the kernel body (vq_tc_impl.cuh) instantiated for the two latent widths of the
 // reference's EVQ-VAEs - D = 64 (VOCASET, MEAD: models/utils/config.py:5-42) and D = 128 (BIWI: config.py:44-60).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 // Converter warps: four at D = 64 (the accumulator-slot cycle MMA -> scan sets the pace there: eight change nothing), eight at
